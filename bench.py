@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — FSK demod + digitize of a synthetic 1 GiSample complex64 capture per B200 (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the reference's own kernels)
+
+One "step" = one pass of the hot path over one capture shard resident in HBM:
+    urh_demod_digitize  (afp_demod FSK + grab_pulse_lens fused, qad materialised)  -> pulse table.
+`value` = whole-job MSamples/s with the IQ already in HBM; `e2e` = the same call fed from pinned HOST
+memory through the public Python API (H2D of the IQ and D2H of the pulse table inside the timed region).
+The capture (8 GiB / GPU) is far larger than the 126 MB L2, so no explicit L2 flush is needed.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SPS = 100
+FS = 2e6
+FDEV = 20e3
+NOISE_MAG = 0.05
+SIGMA = 0.01
+TOL = 5
+CENTER = 0.0
+ALG_BYTES_PER_SAMPLE = 12  # read IQ 8 B + write qad 4 B (pulse table ~0.1 B/sample ignored)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def make_symbols(nsym, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    b = (rng.integers(0, 2, nsym, dtype=np.int8) * 2 - 1).astype(np.int8)
+    s = np.zeros(nsym, dtype=np.int32)
+    np.cumsum(b[:-1], out=s[1:], dtype=np.int32)
+    return b, s
+
+
+class ClockSampler:
+    """Sample nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_arm(n_cpu, steps, warmup, iq_slice=None):
+    """Time the reference's own CPU implementation (oracle/_ref compiled from /root/reference if it travelled
+    here, else the C oracle port) of afp_demod(FSK) + grab_pulse_lens on a bounded slice, all host threads."""
+    from oracle import oracle, ref_loader
+
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    kind = "port"
+    demod, grab = oracle.afp_demod, oracle.grab_pulse_lens
+    try:
+        sf, _, _ = ref_loader.load_kernels()
+        demod = lambda iq, nm, mt, mo: np.asarray(sf.afp_demod(iq, nm, mt, mo))  # noqa: E731
+        grab = lambda q, c, t, mt, sps: np.asarray(sf.grab_pulse_lens(q, c, t, mt, sps))  # noqa: E731
+        kind = "reference"
+    except Exception:
+        oracle.build()
+    if iq_slice is None:
+        iq_slice = host_synth(n_cpu)
+    n_cpu = len(iq_slice)
+    times = []
+    rows = None
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        q = demod(iq_slice, NOISE_MAG, "FSK", 2)
+        rows = grab(q, CENTER, TOL, "FSK", SPS)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    return {"value": n_cpu / sec / 1e6, "unit": "MSamples/s", "cores": cores, "kind": kind,
+            "sample": "%d-sample slice of the same synthetic 2-FSK capture (afp_demod FSK + grab_pulse_lens), mean of %d"
+                      % (n_cpu, len(times)), "ms_per_step": sec * 1e3, "rows": int(len(rows))}
+
+
+def host_synth(n, seed=0):
+    """numpy version of the synthetic recipe for the CPU-only arm (no GPU needed)."""
+    rng = np.random.default_rng(seed)
+    nsym = n // SPS + 2
+    b = rng.integers(0, 2, nsym) * 2 - 1
+    m = np.repeat(b, SPS)[:n]
+    phase = 2 * np.pi * (FDEV / FS) * np.cumsum(m)
+    g = np.arange(n)
+    on = ((g % 6_000_000) < 5_000_000) & (g < int(0.97 * n))
+    x = on * np.exp(1j * phase) + SIGMA * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    iq = np.empty((n, 2), np.float32)
+    iq[:, 0] = x.real
+    iq[:, 1] = x.imag
+    return iq
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=30, help="samples per GPU = 2**log2n (default 1 GiSample)")
+    ap.add_argument("--cpu-log2n", type=int, default=24)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+    n = 1 << args.log2n
+    workload = "2-FSK complex64 2^%d samples/GPU @2MS/s sps=100 +-20kHz AWGN sigma=0.01 bursts+gaps; demod+digitize (center=0, tol=5, noise=0.05)" % args.log2n
+    base = {"metric": "MSamples/s IQ demod+digitize (complex64)", "unit": "MSamples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "samples_per_gpu": n, "l2": "inputs (8 B/sample) larger than L2; no flush"}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference_arm(1 << args.cpu_log2n, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+        line = dict(base)
+        line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"],
+                     "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                     "e2e": {"value": r["value"], "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "gpu_launches": 0})
+        line["config"] = dict(base["config"], reference_sample=r["sample"])
+        print(json.dumps(line))
+        return 0
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # gloo: only barrier + max-reduce of timings (no data-path collective)
+
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    from urh_b200 import _lib
+    from urh_b200.device import DeviceArray, PinnedArray
+    from urh_b200.cythonext import signal_functions as sf
+
+    ctx = _lib.default_context(local_rank)
+    lib = ctx.lib
+    info = ctx.device_info()
+
+    # ---- synthesise this rank's capture directly in HBM ----------------------------------------------------
+    nsym = n // SPS + 2
+    b, s = make_symbols(nsym, seed=1000 + rank)
+    d_b = DeviceArray(ctx, (nsym,), np.int8).set(b)
+    d_s = DeviceArray(ctx, (nsym,), np.int32).set(s)
+    d_iq = DeviceArray(ctx, (n, 2), np.float32)
+    d_qad = DeviceArray(ctx, (n,), np.float32)
+    period, burst = 6_000_000, 5_000_000
+    ctx.check(lib.urh_synth_fsk(ctx.handle, C.c_void_p(d_iq.ptr), n, 0, SPS, C.c_void_p(d_b.ptr), C.c_void_p(d_s.ptr),
+                                C.c_double(FDEV / FS), 1.0, SIGMA, 12345 + rank, period, burst,
+                                int(0.40 * n), int(0.43 * n), int(0.97 * n)))
+    ctx.sync()
+
+    def step_resident():
+        k = C.c_int64(0)
+        ctx.check(lib.urh_demod_digitize(ctx.handle, C.c_void_p(d_iq.ptr), _lib.DT_F32, n, NOISE_MAG, _lib.MOD_FSK,
+                                         CENTER, TOL, SPS, 1, 0.1, C.c_void_p(d_qad.ptr), C.byref(k)))
+        return k.value
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- resident (HBM) timing -----------------------------------------------------------------------------
+    lib.urh_set_profiling(ctx.handle, 1)
+    for _ in range(args.warmup):
+        k_rows = step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    dense_ms = []
+    ctx.timer_start()
+    for _ in range(args.steps):
+        k_rows = step_resident()
+        ms = C.c_float()
+        lib.urh_last_dense_ms(ctx.handle, C.byref(ms))
+        dense_ms.append(ms.value)
+    total_ms = ctx.timer_stop()
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    barrier()
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([total_ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end-to-end through the public API with HOST buffers ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = PinnedArray((n, 2), np.float32, ctx)
+        d_iq.get(out=host.array)  # the capture now lives in pinned host memory
+        d_e2e = DeviceArray(ctx, (n, 2), np.float32)
+        e2e_steps = max(1, min(args.steps, 3))
+
+        def step_e2e():
+            d_e2e.set_async(host.array)
+            qad, rows = sf.demod_digitize(d_e2e, NOISE_MAG, "FSK", CENTER, TOL, SPS, return_qad=False)
+            return rows
+
+        rows = step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        for _ in range(e2e_steps):
+            rows = step_e2e()
+        e2e_ms = ctx.timer_stop()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max(e2e_ms, wall_ms)  # host-side work (D2H of the rows) is part of the step
+        if dist is not None:
+            import torch
+
+            t = torch.tensor([e2e_ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e = {"value": world * n / (e2e_ms / e2e_steps * 1e-3) / 1e6, "unit": "MSamples/s",
+               "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(rows.nbytes), "steps": e2e_steps,
+               "api": "urh_b200.cythonext.signal_functions.demod_digitize(pinned host IQ) -> pulse table on host"}
+        assert len(rows) == k_rows
+        host.free()
+
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel (fused dense demod+classify+run kernel) ---------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dense = float(np.mean(dense_ms))
+    achieved = ALG_BYTES_PER_SAMPLE * n / (dense * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_dense_iq<F32,FSK,DIGITIZE>", "kernel_ms": dense,
+                "algorithmic_bytes_per_launch": ALG_BYTES_PER_SAMPLE * n, "peak_source": peak_src,
+                "kernel_share_of_step": dense / ms_per_step}
+
+    cpu = None
+    if not args.no_cpu:
+        # bounded CPU sample of the same capture (first 2^cpu_log2n samples)
+        ncpu = min(n, 1 << args.cpu_log2n)
+        sl = d_iq[:ncpu].get()
+        r = cpu_reference_arm(ncpu, 2, 1, iq_slice=sl)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = dict(base)
+    line.update({"value": value, "ms_per_step": ms_per_step, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                 "gpu_launches": int(launches), "clocks": clocks, "pulse_rows_per_step": int(k_rows),
+                 "device": info["name"], "sm_count": info["sm_count"]})
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

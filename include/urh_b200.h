@@ -1,0 +1,102 @@
+/*
+ * urh_b200 — C ABI of the B200-native IQ hot path (drop-in for urh.cythonext.* on this path).
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, and returns 0 on success or a
+ * negative URH_ERR_* code (the ctypes shim maps these onto the Python exceptions the reference raises).
+ * Pointers named d_* are DEVICE pointers (from urh_malloc); h_* are HOST pointers.  All work is
+ * enqueued on the context's stream; functions that return a count/scalar synchronise that stream.
+ *
+ * Each function cites the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef URH_B200_H
+#define URH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct urh_ctx urh_ctx;
+
+/* error codes */
+#define URH_OK 0
+#define URH_ERR_CUDA (-1)        /* CUDA runtime / cuFFT / NCCL failure -> RuntimeError            */
+#define URH_ERR_INVALID (-2)     /* bad argument -> ValueError                                      */
+#define URH_ERR_DTYPE (-3)       /* "Unsupported dtype" (signal_functions.pyx:283,354,78)           */
+#define URH_ERR_NOMEM (-4)       /* device allocation failed -> MemoryError                         */
+#define URH_ERR_MODULATION (-5)  /* unknown modulation (assert at signal_functions.pyx:107,111)     */
+#define URH_ERR_NO_DEVICE (-6)   /* no CUDA device: the product has no CPU fallback                 */
+
+/* sample dtypes of the fused `iq` type (util.pxd:1-8) */
+#define URH_DT_I8 0
+#define URH_DT_U8 1
+#define URH_DT_I16 2
+#define URH_DT_U16 3
+#define URH_DT_F32 4
+
+/* modulation types (Signal.MODULATION_TYPES, Signal.py:26; Modulator.MODULATION_TYPES, Modulator.py:21) */
+#define URH_MOD_ASK 0
+#define URH_MOD_FSK 1
+#define URH_MOD_PSK 2
+#define URH_MOD_QAM 3   /* afp_demod leaves zeros for it (signal_functions.pyx:371-376) */
+#define URH_MOD_GFSK 4  /* modulator only */
+#define URH_MOD_OQPSK 5 /* modulator only; digitizer treats it like PSK (signal_functions.pyx:39) */
+
+/* ---- context, memory, timing ------------------------------------------------------------------ */
+int urh_device_count(void);
+int urh_ctx_create(int device, urh_ctx** out);
+void urh_ctx_destroy(urh_ctx* ctx);
+const char* urh_last_error(urh_ctx* ctx);
+int urh_sync(urh_ctx* ctx);
+int urh_device_info(urh_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem, char* name, int name_cap);
+int urh_malloc(urh_ctx* ctx, size_t bytes, void** d_ptr);
+int urh_free(urh_ctx* ctx, void* d_ptr);
+int urh_memset(urh_ctx* ctx, void* d_ptr, int value, size_t bytes);
+int urh_memcpy_h2d(urh_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);   /* async on ctx stream */
+int urh_memcpy_d2h(urh_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);   /* synchronises */
+int urh_memcpy_d2d(urh_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+int urh_host_alloc(urh_ctx* ctx, size_t bytes, void** h_ptr);                      /* pinned */
+int urh_host_free(urh_ctx* ctx, void* h_ptr);
+int urh_timer_start(urh_ctx* ctx);                 /* cudaEventRecord on the ctx stream */
+int urh_timer_stop(urh_ctx* ctx, float* ms);       /* records, synchronises, returns elapsed ms */
+/* number of kernels this library has launched on this context since creation (bench `gpu_launches`) */
+int64_t urh_launch_count(urh_ctx* ctx);
+
+/* ---- demodulation: replaces signal_functions.afp_demod (signal_functions.pyx:333-378) ------------
+ * d_iq: (n,2) C-contiguous samples of `dtype`; d_out: float32[n].  mod_type ASK/FSK computed exactly
+ * as the reference (float32, glibc atan2f restated); PSK -> Costas loop (signal_functions.pyx:252-330);
+ * other -> zeros.  n <= 2 -> zeros (pyx:335). */
+int urh_afp_demod(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_mag, int mod_type,
+                  int mod_order, float costas_loop_bandwidth, float* d_out);
+
+/* thresholds: replaces signal_functions.get_center_thresholds (signal_functions.pyx:380-390); host-only */
+int urh_get_center_thresholds(float center, float spacing, int modulation_order, float* h_out);
+
+/* ---- digitizer: replaces signal_functions.grab_pulse_lens (signal_functions.pyx:392-495) ----------
+ * d_qad float32[n].  Result rows (state, length) int64[k][2] stay in a context-owned device buffer;
+ * *k receives the row count; fetch with urh_fetch_pulses.  */
+int urh_grab_pulse_lens(urh_ctx* ctx, const float* d_qad, int64_t n, float center, uint16_t tolerance,
+                        int mod_type, uint32_t samples_per_symbol, uint8_t bits_per_symbol,
+                        float center_spacing, int64_t* k);
+/* fused a1+a3: demodulate (writes d_qad_out if non-NULL) and digitize in ONE pass over the IQ data. */
+int urh_demod_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_mag, int mod_type,
+                       float center, uint16_t tolerance, uint32_t samples_per_symbol, uint8_t bits_per_symbol,
+                       float center_spacing, float* d_qad_out, int64_t* k);
+int urh_fetch_pulses(urh_ctx* ctx, int64_t* h_rows, int64_t k);          /* D2H of the last result   */
+int urh_pulses_device_ptr(urh_ctx* ctx, const int64_t** d_rows, int64_t* k);
+
+/* ---- measurement utilities (not part of the reference's API surface) -------------------------------- */
+/* CUDA-event timing of the dominant (dense, sample-rate) kernel of the last demod/digitize call */
+int urh_set_profiling(urh_ctx* ctx, int enabled);
+int urh_last_dense_ms(urh_ctx* ctx, float* ms);
+/* synthetic phase-continuous 2-FSK bursts + AWGN + noise-only gaps generated in HBM (SURVEY 8d recipe) */
+int urh_synth_fsk(urh_ctx* ctx, float* d_iq, int64_t n, int64_t global_offset, int sps, const int8_t* d_sym_bit,
+                  const int32_t* d_sym_sum, double dev_ratio, float amplitude, float sigma, uint64_t seed,
+                  int64_t period, int64_t burst, int64_t big_gap_start, int64_t big_gap_end, int64_t tail_start);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* URH_B200_H */

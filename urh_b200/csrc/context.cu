@@ -1,0 +1,271 @@
+// Context, memory, timing and the scratch arena of liburh_b200.
+#include "common.cuh"
+
+extern "C" int urh_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int urh_ctx_create(int device, urh_ctx** out) {
+    if (!out) return URH_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return URH_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return URH_ERR_INVALID;
+    urh_ctx* ctx = new urh_ctx();
+    ctx->device = device;
+    ctx->err[0] = 0;
+    ctx->launches = 0;
+    ctx->arena_block = 0;
+    ctx->arena_used = 0;
+    ctx->arena_need = 0;
+    ctx->pulses = nullptr;
+    ctx->pulses_cap_rows = 0;
+    ctx->pulses_k = 0;
+    ctx->h_mail = nullptr;
+    ctx->h_stage[0] = ctx->h_stage[1] = nullptr;
+    ctx->h_stage_bytes = 0;
+    ctx->fft_valid = false;
+    ctx->nccl_comm = nullptr;
+    ctx->nccl_rank = 0;
+    ctx->nccl_world = 1;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return URH_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return URH_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream[0], cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream[1], cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&ctx->ev_start) == cudaSuccess && cudaEventCreate(&ctx->ev_stop) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++) {
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaEventCreate(&ctx->ev_k0) == cudaSuccess && cudaEventCreate(&ctx->ev_k1) == cudaSuccess;
+    ctx->profiling = 0;
+    ctx->dense_timed = 0;
+    ok = ok && cudaHostAlloc((void**)&ctx->h_mail, 64 * sizeof(int64_t), cudaHostAllocDefault) == cudaSuccess;
+    if (!ok) {
+        delete ctx;
+        return URH_ERR_CUDA;
+    }
+    *out = ctx;
+    return URH_OK;
+}
+
+extern "C" void urh_ctx_destroy(urh_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->arena) cudaFree(b.ptr);
+    if (ctx->pulses) cudaFree(ctx->pulses);
+    if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
+    for (int i = 0; i < 2; i++)
+        if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
+    cudaEventDestroy(ctx->ev_start);
+    cudaEventDestroy(ctx->ev_stop);
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(ctx->ev_copy[i]);
+        cudaEventDestroy(ctx->ev_comp[i]);
+        cudaStreamDestroy(ctx->copy_stream[i]);
+    }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* urh_last_error(urh_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+extern "C" int urh_sync(urh_ctx* ctx) {
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return URH_OK;
+}
+
+extern "C" int urh_device_info(urh_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem,
+                               char* name, int name_cap) {
+    cudaDeviceProp prop;
+    URH_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (total_mem) *total_mem = prop.totalGlobalMem;
+    if (name && name_cap > 0) {
+        strncpy(name, prop.name, name_cap - 1);
+        name[name_cap - 1] = 0;
+    }
+    return URH_OK;
+}
+
+extern "C" int urh_malloc(urh_ctx* ctx, size_t bytes, void** d_ptr) {
+    URH_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (bytes == 0) bytes = 16;
+    URH_CUDA(ctx, cudaMalloc(d_ptr, bytes));
+    return URH_OK;
+}
+
+extern "C" int urh_free(urh_ctx* ctx, void* d_ptr) {
+    if (!d_ptr) return URH_OK;
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    URH_CUDA(ctx, cudaFree(d_ptr));
+    return URH_OK;
+}
+
+extern "C" int urh_memset(urh_ctx* ctx, void* d_ptr, int value, size_t bytes) {
+    URH_CUDA(ctx, cudaMemsetAsync(d_ptr, value, bytes, ctx->stream));
+    return URH_OK;
+}
+
+extern "C" int urh_memcpy_h2d(urh_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    if (bytes == 0) return URH_OK;
+    URH_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return URH_OK;
+}
+
+extern "C" int urh_memcpy_d2h(urh_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    if (bytes) URH_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return URH_OK;
+}
+
+extern "C" int urh_memcpy_d2d(urh_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+    if (bytes == 0) return URH_OK;
+    URH_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return URH_OK;
+}
+
+extern "C" int urh_host_alloc(urh_ctx* ctx, size_t bytes, void** h_ptr) {
+    if (bytes == 0) bytes = 16;
+    URH_CUDA(ctx, cudaHostAlloc(h_ptr, bytes, cudaHostAllocDefault));
+    return URH_OK;
+}
+
+extern "C" int urh_host_free(urh_ctx* ctx, void* h_ptr) {
+    if (h_ptr) URH_CUDA(ctx, cudaFreeHost(h_ptr));
+    return URH_OK;
+}
+
+extern "C" int urh_timer_start(urh_ctx* ctx) {
+    URH_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    return URH_OK;
+}
+
+extern "C" int urh_timer_stop(urh_ctx* ctx, float* ms) {
+    URH_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+    URH_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop));
+    float t = 0.f;
+    URH_CUDA(ctx, cudaEventElapsedTime(&t, ctx->ev_start, ctx->ev_stop));
+    if (ms) *ms = t;
+    return URH_OK;
+}
+
+extern "C" int urh_set_profiling(urh_ctx* ctx, int enabled) {
+    ctx->profiling = enabled ? 1 : 0;
+    ctx->dense_timed = 0;
+    return URH_OK;
+}
+
+extern "C" int urh_last_dense_ms(urh_ctx* ctx, float* ms) {
+    if (!ctx->dense_timed) URH_FAIL(ctx, URH_ERR_INVALID, "no dense kernel timed (enable urh_set_profiling first)");
+    URH_CUDA(ctx, cudaEventSynchronize(ctx->ev_k1));
+    URH_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+    return URH_OK;
+}
+
+extern "C" int64_t urh_launch_count(urh_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- arena ----------------------------------------------------------------------------------------
+// Kernels enqueued earlier may still be reading arena memory when the next op resets the bump pointer;
+// all ops run on the one ctx stream, so reuse is stream-ordered and safe.  Growing (cudaFree) needs a sync.
+void urh_arena_reset(urh_ctx* ctx) {
+    if (ctx->arena.size() > 1) {
+        // coalesce into one block big enough for everything the last op asked for
+        cudaStreamSynchronize(ctx->stream);
+        size_t total = 0;
+        for (auto& b : ctx->arena) {
+            total += b.bytes;
+            cudaFree(b.ptr);
+        }
+        ctx->arena.clear();
+        void* p = nullptr;
+        if (cudaMalloc(&p, total) == cudaSuccess) ctx->arena.push_back({p, total});
+        else cudaGetLastError();
+    }
+    ctx->arena_block = 0;
+    ctx->arena_used = 0;
+    ctx->arena_need = 0;
+}
+
+int urh_arena_alloc(urh_ctx* ctx, size_t bytes, void** out) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    ctx->arena_need += bytes;
+    while (ctx->arena_block < ctx->arena.size()) {
+        urh_block& b = ctx->arena[ctx->arena_block];
+        if (ctx->arena_used + bytes <= b.bytes) {
+            *out = (char*)b.ptr + ctx->arena_used;
+            ctx->arena_used += bytes;
+            return URH_OK;
+        }
+        ctx->arena_block++;
+        ctx->arena_used = 0;
+    }
+    size_t want = bytes > ((size_t)64 << 20) ? bytes : ((size_t)64 << 20);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess && want > bytes) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        snprintf(ctx->err, sizeof(ctx->err), "arena: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        return URH_ERR_NOMEM;
+    }
+    ctx->arena.push_back({p, want});
+    ctx->arena_block = ctx->arena.size() - 1;
+    ctx->arena_used = bytes;
+    *out = p;
+    return URH_OK;
+}
+
+int urh_ensure_pulses(urh_ctx* ctx, size_t rows) {
+    if (rows < 16) rows = 16;
+    if (rows <= ctx->pulses_cap_rows) return URH_OK;
+    if (ctx->pulses) {
+        URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        URH_CUDA(ctx, cudaFree(ctx->pulses));
+        ctx->pulses = nullptr;
+        ctx->pulses_cap_rows = 0;
+    }
+    size_t cap = rows + rows / 4;
+    URH_CUDA(ctx, cudaMalloc((void**)&ctx->pulses, cap * 2 * sizeof(int64_t)));
+    ctx->pulses_cap_rows = cap;
+    return URH_OK;
+}
+
+int urh_ensure_stage(urh_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->h_stage_bytes) return URH_OK;
+    for (int i = 0; i < 2; i++) {
+        if (ctx->h_stage[i]) URH_CUDA(ctx, cudaFreeHost(ctx->h_stage[i]));
+        ctx->h_stage[i] = nullptr;
+    }
+    ctx->h_stage_bytes = 0;
+    for (int i = 0; i < 2; i++) URH_CUDA(ctx, cudaHostAlloc(&ctx->h_stage[i], bytes, cudaHostAllocDefault));
+    ctx->h_stage_bytes = bytes;
+    return URH_OK;
+}
+
+int urh_read_i64(urh_ctx* ctx, const int64_t* d_src, int count, int64_t* h_out) {
+    if (count > 64) return URH_ERR_INVALID;
+    URH_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, d_src, count * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < count; i++) h_out[i] = ctx->h_mail[i];
+    return URH_OK;
+}

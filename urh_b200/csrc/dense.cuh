@@ -1,0 +1,215 @@
+// The dense (sample-rate) pass shared by demodulation, digitizing and message segmentation.
+//
+// Layout: the sample stream is cut into TILES of URH_TILE consecutive samples, one warp per tile.
+// A warp walks its tile 64 samples at a time; lane l owns samples (2l, 2l+1) of each 64-group, i.e.
+// one 128-bit load of two float2 IQ samples (fully coalesced: 512 B per warp per step) and one 64-bit
+// store of two demodulated floats.  The FSK predecessor sample comes from the neighbouring lane by
+// shuffle, never from a second load.
+//
+// The digitizer state machine of the reference (signal_functions.pyx:431-483) is restated in terms of
+// RUNS of equal class: a run produces a CANDIDATE at run_start + tolerance iff
+// it is longer than `tolerance`.  Class boundaries are found with warp ballots, and the (warp-uniform)
+// boundary bit-mask is walked by the whole warp in lock-step, so the per-sample cost of the state
+// machine is two compares and two votes.  Runs that touch a tile edge are summarised (class, length)
+// and stitched by a scan over the tile table (digitize.cu), which makes the decomposition exact for
+// any tolerance.
+#pragma once
+#include "common.cuh"
+#include "fdlibm_atan2f.h"
+
+#define URH_TILE 2048          // samples per warp-tile (multiple of 64, < 65536)
+#define URH_WARPS_PER_BLOCK 8
+#define URH_MAX_THR 255
+
+struct UrhClassify {
+    float noise_value;     // exact-equality sentinel (signal_functions.pyx:435)
+    int order;             // 2**bits_per_symbol
+    float thr[URH_MAX_THR];  // get_center_thresholds (signal_functions.pyx:380-390)
+};
+
+struct __align__(16) UrhTileSummary {
+    int16_t first_cls;
+    int16_t last_cls;
+    int32_t head_len;   // length of the run containing the tile's first sample (== tile_len if whole)
+    int32_t tail_len;   // length (inside the tile) of the run containing the tile's last sample
+    int32_t ncand;      // interior candidates written to the staging area
+};
+
+// ---- IQ sample access ------------------------------------------------------------------------------
+template <int DT> struct UrhElem;
+template <> struct UrhElem<URH_DT_I8> { typedef int8_t type; };
+template <> struct UrhElem<URH_DT_U8> { typedef uint8_t type; };
+template <> struct UrhElem<URH_DT_I16> { typedef int16_t type; };
+template <> struct UrhElem<URH_DT_U16> { typedef uint16_t type; };
+template <> struct UrhElem<URH_DT_F32> { typedef float type; };
+
+struct UrhPair {
+    float r0, i0, r1, i1;
+};
+
+__device__ __forceinline__ float4 urh_ldg_f4(const void* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 urh_ldg_u2(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t urh_ldg_u1(const void* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void urh_stg_f2(float* p, float a, float b) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// Load samples (i, i+1) of an (n,2) array.  `vec` = base pointer is aligned for a two-sample vector load.
+template <int DT>
+__device__ __forceinline__ UrhPair urh_load_pair(const void* base, int64_t i, int64_t n, bool vec) {
+    typedef typename UrhElem<DT>::type E;
+    const E* p = (const E*)base + 2 * i;
+    UrhPair o;
+    o.r0 = o.i0 = o.r1 = o.i1 = 0.0f;
+    if (i + 1 < n && vec) {
+        if (DT == URH_DT_F32) {
+            const float4 v = urh_ldg_f4(p);
+            o.r0 = v.x; o.i0 = v.y; o.r1 = v.z; o.i1 = v.w;
+        } else if (DT == URH_DT_I16) {
+            const uint2 v = urh_ldg_u2(p);
+            o.r0 = (float)(int16_t)(v.x & 0xffff); o.i0 = (float)(int16_t)(v.x >> 16);
+            o.r1 = (float)(int16_t)(v.y & 0xffff); o.i1 = (float)(int16_t)(v.y >> 16);
+        } else if (DT == URH_DT_U16) {
+            const uint2 v = urh_ldg_u2(p);
+            o.r0 = (float)(v.x & 0xffff); o.i0 = (float)(v.x >> 16);
+            o.r1 = (float)(v.y & 0xffff); o.i1 = (float)(v.y >> 16);
+        } else if (DT == URH_DT_I8) {
+            const uint32_t v = urh_ldg_u1(p);
+            o.r0 = (float)(int8_t)(v & 0xff); o.i0 = (float)(int8_t)((v >> 8) & 0xff);
+            o.r1 = (float)(int8_t)((v >> 16) & 0xff); o.i1 = (float)(int8_t)(v >> 24);
+        } else {
+            const uint32_t v = urh_ldg_u1(p);
+            o.r0 = (float)(v & 0xff); o.i0 = (float)((v >> 8) & 0xff);
+            o.r1 = (float)((v >> 16) & 0xff); o.i1 = (float)(v >> 24);
+        }
+    } else {
+        if (i < n) { o.r0 = (float)__ldg(p); o.i0 = (float)__ldg(p + 1); }
+        if (i + 1 < n) { o.r1 = (float)__ldg(p + 2); o.i1 = (float)__ldg(p + 3); }
+    }
+    return o;
+}
+
+// ---- demodulation of one sample (bit-faithful to signal_functions.pyx:363-376) ---------------------
+struct UrhDemodParams {
+    float noise_sqrd;   // noise_mag * noise_mag (float)
+    float noise_value;  // NOISE sentinel
+    float max_mag;      // ASK normalisation (pyx:343-352)
+};
+
+template <int MOD>
+__device__ __forceinline__ float urh_demod_one(float pr, float pi, float re, float im, const UrhDemodParams& P) {
+    const float mag = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+    if (mag <= P.noise_sqrd) return P.noise_value;
+    if (MOD == URH_MOD_ASK) {
+        return __fdiv_rn(__fsqrt_rn(mag), P.max_mag);
+    } else if (MOD == URH_MOD_FSK) {
+        // tmp = (a - 1j*b) * (c + 1j*d) evaluated exactly as the C++ std::complex<float> expression:
+        // 1j*v = (0*v - 1*0, 0*0 + 1*v); real -/+ complex acts on (real, 0).  Signed zeros matter.
+        const float tr = __fsub_rn(__fmul_rn(0.0f, pi), 0.0f);
+        const float ti = __fadd_rn(0.0f, pi);
+        const float A = __fsub_rn(pr, tr);
+        const float B = __fsub_rn(0.0f, ti);
+        const float ur = __fsub_rn(__fmul_rn(0.0f, im), 0.0f);
+        const float ui = __fadd_rn(0.0f, im);
+        const float C = __fadd_rn(re, ur);
+        const float D = __fadd_rn(0.0f, ui);
+        const float xr = __fsub_rn(__fmul_rn(A, C), __fmul_rn(B, D));
+        const float xi = __fadd_rn(__fmul_rn(A, D), __fmul_rn(B, C));
+        return urh_atan2f(xi, xr);
+    } else {
+        return 0.0f;
+    }
+}
+
+// ---- classification (signal_functions.pyx:435-442) --------------------------------------------------
+__device__ __forceinline__ int urh_classify(float s, const UrhClassify& C) {
+    if (s == C.noise_value) return -1;
+    if (C.order == 2) return (s <= C.thr[0]) ? 0 : 1;
+    int c = C.order - 1;
+    for (int k = 0; k < C.order - 1; k++) {
+        if (s <= C.thr[k]) { c = k; break; }
+    }
+    return c;
+}
+
+// ---- warp-uniform run tracker -------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t urh_spread_bits(uint32_t x) {
+    uint64_t v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+struct UrhRunTracker {
+    int tol;
+    int run_start, run_cls, first_cls, head_len, ncand, carry_cls;
+    bool is_head;
+    uint32_t* stage;   // this tile's staging slots
+
+    __device__ __forceinline__ void init(int tol_, uint32_t* stage_) {
+        tol = tol_; stage = stage_;
+        run_start = 0; run_cls = -2; first_cls = -2; head_len = 0; ncand = 0; carry_cls = -2; is_head = true;
+    }
+    __device__ __forceinline__ void emit(int pos, int cls, int lane) {
+        if (lane == 0) stage[ncand] = ((uint32_t)pos << 16) | (uint32_t)(cls + 1);
+        ncand++;
+    }
+    // c0,c1: classes of this lane's two samples of 64-group `it`; v0,v1: sample exists (inside the tile)
+    __device__ __forceinline__ void feed(int it, int c0, int c1, bool v0, bool v1, int lane) {
+        int pc = __shfl_up_sync(URH_FULL_MASK, c1, 1);
+        if (lane == 0) pc = carry_cls;
+        const bool b0 = v0 && (c0 != pc);
+        const bool b1 = v1 && (c1 != c0);
+        carry_cls = __shfl_sync(URH_FULL_MASK, c1, 31);
+        const uint32_t m0 = __ballot_sync(URH_FULL_MASK, b0);
+        const uint32_t m1 = __ballot_sync(URH_FULL_MASK, b1);
+        if ((m0 | m1) == 0u) return;
+        uint64_t bits = urh_spread_bits(m0) | (urh_spread_bits(m1) << 1);
+        while (bits) {
+            const int bit = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            const int p = it * 64 + bit;
+            const int cls_p = __shfl_sync(URH_FULL_MASK, (bit & 1) ? c1 : c0, bit >> 1);
+            if (run_cls == -2) {
+                first_cls = cls_p;                    // the forced boundary at p == 0 opens the head run
+            } else if (is_head) {
+                head_len = p;
+                is_head = false;
+            } else if (p - run_start > tol) {
+                emit(run_start + tol, run_cls, lane);
+            }
+            run_start = p;
+            run_cls = cls_p;
+        }
+    }
+    __device__ __forceinline__ void finish(int tile_len, UrhTileSummary* out, int lane) {
+        if (is_head) head_len = tile_len;
+        else if (tile_len - run_start > tol) emit(run_start + tol, run_cls, lane);
+        if (lane == 0) {
+            UrhTileSummary s;
+            s.first_cls = (int16_t)first_cls;
+            s.last_cls = (int16_t)run_cls;
+            s.head_len = head_len;
+            s.tail_len = tile_len - run_start;
+            s.ncand = ncand;
+            *out = s;
+        }
+    }
+};

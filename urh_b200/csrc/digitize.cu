@@ -1,0 +1,336 @@
+// afp_demod (ASK/FSK), grab_pulse_lens and the fused demod+digitize path.
+//
+// Reference: src/urh/cythonext/signal_functions.pyx:333-378 (afp_demod), :392-495 (grab_pulse_lens).
+// See dense.cuh for the dense pass and DESIGN.md for the run/candidate restatement of the digitizer.
+#include "dense.cuh"
+#include "scan.cuh"
+#include "sparse.cuh"
+
+#include <math.h>
+
+// =====================================================================================================
+// Dense kernels
+// =====================================================================================================
+
+// IQ source: demodulate (+ optionally write qad, + optionally digitize).
+template <int DT, int MOD, bool DIGITIZE>
+__global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32)
+k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __restrict__ qad_out, int vec_in,
+           int vec_out, const __grid_constant__ UrhClassify cls, int tol, UrhTileSummary* __restrict__ tiles,
+           uint32_t* __restrict__ staging, int stage_cap, int16_t* __restrict__ init_cls, int cls_of_zero) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * URH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int64_t tile_start = tile * URH_TILE;
+    if (tile_start >= n) return;
+    const int tile_len = (int)((n - tile_start) < URH_TILE ? (n - tile_start) : URH_TILE);
+    const int iters = (tile_len + 63) >> 6;
+
+    UrhRunTracker rt;
+    if (DIGITIZE) rt.init(tol, staging + tile * (int64_t)stage_cap);
+
+    // FSK predecessor of the tile's first sample
+    float cr = 0.0f, ci = 0.0f;
+    if (MOD == URH_MOD_FSK && tile_start > 0 && lane == 0) {
+        const UrhPair pv = urh_load_pair<DT>(iq, tile_start - 1, n, false);
+        cr = pv.r0; ci = pv.i0;
+    }
+
+    UrhPair cur = urh_load_pair<DT>(iq, tile_start + 2 * lane, n, vec_in != 0);
+    for (int it = 0; it < iters; it++) {
+        const int64_t pos0 = tile_start + (int64_t)it * 64 + 2 * lane;
+        UrhPair nxt;
+        if (it + 1 < iters) nxt = urh_load_pair<DT>(iq, pos0 + 64, n, vec_in != 0);
+
+        float pr = 0.0f, pi = 0.0f;
+        if (MOD == URH_MOD_FSK) {
+            pr = __shfl_up_sync(URH_FULL_MASK, cur.r1, 1);
+            pi = __shfl_up_sync(URH_FULL_MASK, cur.i1, 1);
+            if (lane == 0) { pr = cr; pi = ci; }
+            cr = __shfl_sync(URH_FULL_MASK, cur.r1, 31);
+            ci = __shfl_sync(URH_FULL_MASK, cur.i1, 31);
+        }
+        float s0 = urh_demod_one<MOD>(pr, pi, cur.r0, cur.i0, dp);
+        const float s1 = urh_demod_one<MOD>(cur.r0, cur.i0, cur.r1, cur.i1, dp);
+        if (pos0 == 0) s0 = dp.noise_value;  // result[0] = NOISE (pyx:361)
+
+        const bool v0 = pos0 < n, v1 = pos0 + 1 < n;
+        if (qad_out) {
+            if (v1 && vec_out) urh_stg_f2(qad_out + pos0, s0, s1);
+            else {
+                if (v0) qad_out[pos0] = s0;
+                if (v1) qad_out[pos0 + 1] = s1;
+            }
+        }
+        if (DIGITIZE) {
+            const int c0 = urh_classify(s0, cls), c1 = urh_classify(s1, cls);
+            if (pos0 == 0) *init_cls = (int16_t)((s0 == cls.noise_value) ? -1 : cls_of_zero);
+            rt.feed(it, c0, c1, v0, v1, lane);
+        }
+        cur = nxt;
+    }
+    if (DIGITIZE) rt.finish(tile_len, tiles + tile, lane);
+}
+
+// Classifier sources for the stand-alone digitizer / segmenter: float32 samples already in memory.
+struct SrcQad {  // grab_pulse_lens on a demodulated array
+    __device__ __forceinline__ static int cls(float s, const UrhClassify& C) { return urh_classify(s, C); }
+};
+struct SrcAbove {  // segment_messages_from_magnitudes: class 1 = above noise (auto_interpretation.pyx:79)
+    __device__ __forceinline__ static int cls(float s, const UrhClassify& C) { return (s > C.thr[0]) ? 1 : 0; }
+};
+struct SrcCenter {  // get_plateau_lengths: -1/1 around center (auto_interpretation.pyx:183,197) as 0/1
+    __device__ __forceinline__ static int cls(float s, const UrhClassify& C) { return (s <= C.thr[0]) ? 0 : 1; }
+};
+
+template <typename SRC>
+__global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32)
+k_dense_f32(const float* __restrict__ x, int64_t n, int vec_in, const __grid_constant__ UrhClassify cls, int tol,
+            UrhTileSummary* __restrict__ tiles, uint32_t* __restrict__ staging, int stage_cap,
+            int16_t* __restrict__ init_cls, int cls_of_zero) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * URH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int64_t tile_start = tile * URH_TILE;
+    if (tile_start >= n) return;
+    const int tile_len = (int)((n - tile_start) < URH_TILE ? (n - tile_start) : URH_TILE);
+    const int iters = (tile_len + 63) >> 6;
+    UrhRunTracker rt;
+    rt.init(tol, staging + tile * (int64_t)stage_cap);
+    // two 64-groups in flight per warp step
+    for (int it = 0; it < iters; it += 2) {
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+        const int64_t pa = tile_start + (int64_t)it * 64 + 2 * lane;
+        const int64_t pb = pa + 64;
+        if (vec_in && pa + 1 < n) {
+            const float2 v = __ldg((const float2*)(x + pa));
+            a0 = v.x; a1 = v.y;
+        } else {
+            if (pa < n) a0 = __ldg(x + pa);
+            if (pa + 1 < n) a1 = __ldg(x + pa + 1);
+        }
+        const bool has_b = it + 1 < iters;
+        if (has_b) {
+            if (vec_in && pb + 1 < n) {
+                const float2 v = __ldg((const float2*)(x + pb));
+                b0 = v.x; b1 = v.y;
+            } else {
+                if (pb < n) b0 = __ldg(x + pb);
+                if (pb + 1 < n) b1 = __ldg(x + pb + 1);
+            }
+        }
+        if (pa == 0 && init_cls) *init_cls = (int16_t)((a0 == cls.noise_value) ? -1 : cls_of_zero);
+        rt.feed(it, SRC::cls(a0, cls), SRC::cls(a1, cls), pa < n, pa + 1 < n, lane);
+        if (has_b) rt.feed(it + 1, SRC::cls(b0, cls), SRC::cls(b1, cls), pb < n, pb + 1 < n, lane);
+    }
+    rt.finish(tile_len, tiles + tile, lane);
+}
+
+// =====================================================================================================
+// Host side
+// =====================================================================================================
+
+extern "C" int urh_get_center_thresholds(float center, float spacing, int modulation_order, float* h_out) {
+    // signal_functions.pyx:380-390 — float32 arithmetic on (int * float)
+    const int n = modulation_order / 2;
+    for (int i = 0; i < n; i++) {
+        volatile float t = (float)(n - (i + 1)) * spacing;
+        h_out[i] = center - t;
+    }
+    for (int i = n; i < modulation_order - 1; i++) {
+        volatile float t = (float)(i + 1 - n) * spacing;
+        h_out[i] = center + t;
+    }
+    return URH_OK;
+}
+
+static int fill_classify(urh_ctx* ctx, UrhClassify* C, int mod_type, float center, uint8_t bits_per_symbol,
+                         float spacing) {
+    if (bits_per_symbol > 8) URH_FAIL(ctx, URH_ERR_INVALID, "bits_per_symbol %d > 8 not supported", (int)bits_per_symbol);
+    memset(C, 0, sizeof(*C));
+    C->noise_value = urh_noise_value(mod_type);
+    C->order = 1 << bits_per_symbol;
+    if (C->order > 1) urh_get_center_thresholds(center, spacing, C->order, C->thr);
+    return URH_OK;
+}
+
+static int host_classify(float s, const UrhClassify& C) {
+    int c = C.order - 1;
+    for (int k = 0; k < C.order - 1; k++)
+        if (s <= C.thr[k]) { c = k; break; }
+    return c;
+}
+
+static float max_magnitude_for(int dtype) {
+    // signal_functions.pyx:343-352: double sqrt of an integer constant, stored in a float
+    switch (dtype) {
+        case URH_DT_I8: return (float)sqrt(127.0 * 127.0 + 128.0 * 128.0);
+        case URH_DT_U8: return (float)sqrt(255.0 * 255.0);
+        case URH_DT_I16: return (float)sqrt(32768.0 * 32768.0 + 32767.0 * 32767.0);
+        case URH_DT_U16: return (float)sqrt(65535.0 * 65535.0);
+        default: return (float)sqrt(2.0);
+    }
+}
+
+static bool iq_vec_aligned(const void* p, int dtype) { return ((uintptr_t)p % (2 * (size_t)urh_iq_bytes(dtype))) == 0; }
+
+template <int DT, int MOD, bool DIG>
+static int launch_dense_iq_t(urh_ctx* ctx, const void* d_iq, int64_t n, const UrhDemodParams& dp, float* d_qad,
+                             const UrhClassify& cls, int tol, UrhTileSummary* tiles, uint32_t* staging,
+                             int stage_cap, int16_t* init_cls, int cls_of_zero) {
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    const unsigned grid = (unsigned)urh_div_up(ntiles, URH_WARPS_PER_BLOCK);
+    const int vec_in = iq_vec_aligned(d_iq, DT) ? 1 : 0;
+    const int vec_out = (d_qad && ((uintptr_t)d_qad % 8) == 0) ? 1 : 0;
+    URH_PROF_BEGIN(ctx);
+    URH_LAUNCH(ctx, (k_dense_iq<DT, MOD, DIG>), grid, URH_WARPS_PER_BLOCK * 32, 0, d_iq, n, dp, d_qad, vec_in,
+               vec_out, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero);
+    URH_PROF_END(ctx);
+    return URH_OK;
+}
+
+template <int MOD, bool DIG>
+static int launch_dense_iq_m(urh_ctx* ctx, int dtype, const void* d_iq, int64_t n, const UrhDemodParams& dp,
+                             float* d_qad, const UrhClassify& cls, int tol, UrhTileSummary* tiles,
+                             uint32_t* staging, int stage_cap, int16_t* init_cls, int cls_of_zero) {
+    switch (dtype) {
+        case URH_DT_I8: return launch_dense_iq_t<URH_DT_I8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero);
+        case URH_DT_U8: return launch_dense_iq_t<URH_DT_U8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero);
+        case URH_DT_I16: return launch_dense_iq_t<URH_DT_I16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero);
+        case URH_DT_U16: return launch_dense_iq_t<URH_DT_U16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero);
+        case URH_DT_F32: return launch_dense_iq_t<URH_DT_F32, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero);
+        default: URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
+    }
+}
+
+int urh_costas_demod(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_sqrd, int loop_order,
+                     float bandwidth, float* d_out);  // costas.cu
+
+static UrhDemodParams make_demod_params(float noise_mag, int mod_type, int dtype) {
+    UrhDemodParams dp;
+    volatile float nm = noise_mag;
+    volatile float sq = nm * nm;
+    dp.noise_sqrd = sq;
+    dp.noise_value = urh_noise_value(mod_type);
+    dp.max_mag = max_magnitude_for(dtype);
+    return dp;
+}
+
+extern "C" int urh_afp_demod(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_mag, int mod_type,
+                             int mod_order, float costas_loop_bandwidth, float* d_out) {
+    if (n < 0) URH_FAIL(ctx, URH_ERR_INVALID, "negative length");
+    if (urh_iq_bytes(dtype) == 0) URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
+    if (n == 0) return URH_OK;
+    if (n <= 2 || (mod_type != URH_MOD_ASK && mod_type != URH_MOD_FSK && mod_type != URH_MOD_PSK)) {
+        // pyx:335-336 (short input) and pyx:360,371-376 (unknown mod_type leaves zeros, result[0] = NOISE)
+        URH_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(float), ctx->stream));
+        if (n > 2) {
+            const float nv = urh_noise_value(mod_type);
+            URH_CUDA(ctx, cudaMemcpyAsync(d_out, &nv, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+            URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        return URH_OK;
+    }
+    const UrhDemodParams dp = make_demod_params(noise_mag, mod_type, dtype);
+    if (mod_type == URH_MOD_PSK) return urh_costas_demod(ctx, d_iq, dtype, n, dp.noise_sqrd, mod_order, costas_loop_bandwidth, d_out);
+    UrhClassify cls;
+    memset(&cls, 0, sizeof(cls));
+    if (mod_type == URH_MOD_ASK)
+        return launch_dense_iq_m<URH_MOD_ASK, false>(ctx, dtype, d_iq, n, dp, d_out, cls, 0, nullptr, nullptr, 0, nullptr, 0);
+    return launch_dense_iq_m<URH_MOD_FSK, false>(ctx, dtype, d_iq, n, dp, d_out, cls, 0, nullptr, nullptr, 0, nullptr, 0);
+}
+
+// Shared tail of the two digitizer entry points: tile table + staging -> merged (state, length) rows.
+static int digitize_finish(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t sps, UrhTileSummary* tiles,
+                           uint32_t* staging, int stage_cap, int16_t* d_init, int64_t* k) {
+    UrhCandidates cand;
+    URH_CHECK(urh_collect_candidates(ctx, n, tol, tiles, staging, stage_cap, &cand));
+    return urh_pulses_from_candidates(ctx, n, tol, is_ask, sps, cand, d_init, k);
+}
+
+static int stage_cap_for(int tol) { return URH_TILE / (tol + 1) + 2; }
+
+extern "C" int urh_grab_pulse_lens(urh_ctx* ctx, const float* d_qad, int64_t n, float center, uint16_t tolerance,
+                                   int mod_type, uint32_t samples_per_symbol, uint8_t bits_per_symbol,
+                                   float center_spacing, int64_t* k) {
+    if (!k) return URH_ERR_INVALID;
+    *k = 0;
+    ctx->pulses_k = 0;
+    if (n < 0) URH_FAIL(ctx, URH_ERR_INVALID, "negative length");
+    if (n == 0) return URH_OK;  // pyx:416-417 -> empty (0,2) table
+    urh_arena_reset(ctx);
+    UrhClassify cls;
+    URH_CHECK(fill_classify(ctx, &cls, mod_type, center, bits_per_symbol, center_spacing));
+    const int tol = tolerance;
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    const int cap = stage_cap_for(tol);
+    UrhTileSummary* tiles;
+    uint32_t* staging;
+    int16_t* d_init;
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles, &tiles));
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles * cap, &staging));
+    URH_CHECK(urh_arena(ctx, 8, &d_init));
+    const unsigned grid = (unsigned)urh_div_up(ntiles, URH_WARPS_PER_BLOCK);
+    const int vec_in = (((uintptr_t)d_qad % 8) == 0) ? 1 : 0;
+    URH_PROF_BEGIN(ctx);
+    URH_LAUNCH(ctx, (k_dense_f32<SrcQad>), grid, URH_WARPS_PER_BLOCK * 32, 0, d_qad, n, vec_in, cls, tol, tiles,
+               staging, cap, d_init, host_classify(0.0f, cls));
+    URH_PROF_END(ctx);
+    return digitize_finish(ctx, n, tol, mod_type == URH_MOD_ASK, samples_per_symbol, tiles, staging, cap, d_init, k);
+}
+
+extern "C" int urh_demod_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_mag,
+                                  int mod_type, float center, uint16_t tolerance, uint32_t samples_per_symbol,
+                                  uint8_t bits_per_symbol, float center_spacing, float* d_qad_out, int64_t* k) {
+    if (!k) return URH_ERR_INVALID;
+    *k = 0;
+    ctx->pulses_k = 0;
+    if (n < 0) URH_FAIL(ctx, URH_ERR_INVALID, "negative length");
+    if (urh_iq_bytes(dtype) == 0) URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
+    if (n == 0) return URH_OK;
+    if (n <= 2 || (mod_type != URH_MOD_ASK && mod_type != URH_MOD_FSK)) {
+        // not a fusable case: run the two reference steps back to back (PSK is a serial recurrence)
+        float* q = d_qad_out;
+        if (!q) URH_CUDA(ctx, cudaMalloc((void**)&q, (size_t)n * sizeof(float)));
+        int rc = urh_afp_demod(ctx, d_iq, dtype, n, noise_mag, mod_type, 1 << bits_per_symbol, 0.1f, q);
+        if (rc == URH_OK)
+            rc = urh_grab_pulse_lens(ctx, q, n, center, tolerance, mod_type, samples_per_symbol, bits_per_symbol,
+                                     center_spacing, k);
+        if (!d_qad_out) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(q);
+        }
+        return rc;
+    }
+    urh_arena_reset(ctx);
+    UrhClassify cls;
+    URH_CHECK(fill_classify(ctx, &cls, mod_type, center, bits_per_symbol, center_spacing));
+    const UrhDemodParams dp = make_demod_params(noise_mag, mod_type, dtype);
+    const int tol = tolerance;
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    const int cap = stage_cap_for(tol);
+    UrhTileSummary* tiles;
+    uint32_t* staging;
+    int16_t* d_init;
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles, &tiles));
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles * cap, &staging));
+    URH_CHECK(urh_arena(ctx, 8, &d_init));
+    const int c0 = host_classify(0.0f, cls);
+    if (mod_type == URH_MOD_ASK)
+        URH_CHECK((launch_dense_iq_m<URH_MOD_ASK, true>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, tol, tiles, staging, cap, d_init, c0)));
+    else
+        URH_CHECK((launch_dense_iq_m<URH_MOD_FSK, true>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, tol, tiles, staging, cap, d_init, c0)));
+    return digitize_finish(ctx, n, tol, mod_type == URH_MOD_ASK, samples_per_symbol, tiles, staging, cap, d_init, k);
+}
+
+extern "C" int urh_fetch_pulses(urh_ctx* ctx, int64_t* h_rows, int64_t k) {
+    if (k < 0 || k > ctx->pulses_k) URH_FAIL(ctx, URH_ERR_INVALID, "fetch_pulses: k=%lld exceeds last result %lld", (long long)k, (long long)ctx->pulses_k);
+    if (k == 0) return URH_OK;
+    URH_CUDA(ctx, cudaMemcpyAsync(h_rows, ctx->pulses, (size_t)k * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return URH_OK;
+}
+
+extern "C" int urh_pulses_device_ptr(urh_ctx* ctx, const int64_t** d_rows, int64_t* k) {
+    if (d_rows) *d_rows = ctx->pulses;
+    if (k) *k = ctx->pulses_k;
+    return URH_OK;
+}

@@ -1,0 +1,20 @@
+// Sparse stages shared by the digitizer, the message segmenter and the plateau RLE:
+// tile summaries + per-tile staged candidates  ->  one ordered, compact candidate table.
+#pragma once
+#include "dense.cuh"
+
+struct UrhCandidates {
+    int64_t count;   // number of candidates (host copy)
+    int64_t* pos;    // device: absolute sample index run_start + tolerance
+    int16_t* cls;    // device: class of the run
+};
+
+// Stitch runs across tile edges (scan over the tile table), add the per-tile head candidates and gather
+// everything into `out` (arena memory).  Synchronises once to learn the candidate count.
+int urh_collect_candidates(urh_ctx* ctx, int64_t n, int tol, const UrhTileSummary* tiles, const uint32_t* staging,
+                           int stage_cap, UrhCandidates* out);
+
+// grab_pulse_lens tail (signal_functions.pyx:455-495) on the candidate table: fire filter, pulse lengths,
+// ASK short-pause relabel, merge of equal neighbours, tail row.  Result -> ctx->pulses / ctx->pulses_k.
+int urh_pulses_from_candidates(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t sps, const UrhCandidates& cand,
+                               const int16_t* d_init_cls, int64_t* k);
