@@ -14,6 +14,9 @@ HARNESS = r"""
 void restated_atan2f(const float* y, const float* x, float* out, long n) {
     for (long i = 0; i < n; i++) out[i] = urh_atan2f(y[i], x[i]);
 }
+void restated_atan2f_v2(const float* y, const float* x, float* out, long n) {
+    for (long i = 0; i < n; i++) out[i] = urh_atan2f_v2(y[i], x[i]);
+}
 """
 
 
@@ -39,6 +42,10 @@ def test_atan2f_bit_exact_vs_libm():
         parts_x.append((rng.integers(-32768, 32768, n)).astype(np.float32))
         parts_y.append((rng.standard_normal(n) * 2.0 ** rng.integers(-40, 40, n)).astype(np.float32))
         parts_x.append((rng.standard_normal(n) * 2.0 ** rng.integers(-40, 40, n)).astype(np.float32))
+        parts_y.append((rng.standard_normal(n) * 2.0 ** rng.integers(-120, 120, n)).astype(np.float32))
+        parts_x.append((rng.standard_normal(n) * 2.0 ** rng.integers(-120, 120, n)).astype(np.float32))
+        parts_y.append(rng.integers(-4, 5, n).astype(np.float32) * rng.choice([1.0, -1.0, 0.0, -0.0], n).astype(np.float32))
+        parts_x.append(rng.integers(-4, 5, n).astype(np.float32) * rng.choice([1.0, -1.0, 1.0, -0.0], n).astype(np.float32))
         special = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, 1e-45, -1e-45, 3.4e38, 0.4375, 0.6875, 1.1875, 2.4375, 2.0**25, 2.0**-29], dtype=np.float32)
         sy, sx = np.meshgrid(special, special)
         parts_y.append(sy.ravel())
@@ -57,3 +64,8 @@ def test_atan2f_bit_exact_vs_libm():
         nan = np.isnan(ref)
         assert np.array_equal(np.isnan(out), nan)
         assert np.array_equal(out.view(np.uint32)[~nan], ref.view(np.uint32)[~nan])
+        # the branch-light variant the FSK kernel actually calls
+        out2 = np.empty_like(y)
+        lib.restated_atan2f_v2(y.ctypes.data_as(ctypes.c_void_p), x.ctypes.data_as(ctypes.c_void_p), out2.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(len(y)))
+        assert np.array_equal(np.isnan(out2), nan)
+        assert np.array_equal(out2.view(np.uint32)[~nan], ref.view(np.uint32)[~nan])

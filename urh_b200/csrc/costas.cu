@@ -6,6 +6,7 @@
 // the next chunk of samples (converted, noise-gated, scaled) into shared memory and writes the previous
 // chunk of results back with coalesced stores, so the serial lane never waits on global memory.
 #include "dense.cuh"
+#include "glibc_sincosf.h"
 
 #include <math.h>
 
@@ -61,8 +62,11 @@ __global__ void __launch_bounds__(32) k_costas(const void* __restrict__ iq, int6
                 // current_sample = rf + 1j*jf  (std::complex<float> arithmetic, as in urh_demod_one)
                 const float cs_r = __fadd_rn(rf, __fsub_rn(__fmul_rn(0.0f, jf), 0.0f));
                 const float cs_i = __fadd_rn(0.0f, __fadd_rn(0.0f, jf));
+                // glibc 2.39 sinf/cosf restated bit-for-bit (glibc_sincosf.h); |phase| <= 2*pi + 2 < 120 always
                 float sn, cn;
-                sincosf(-phase, &sn, &cn);
+                int sc_ok;
+                urh_glibc_sincosf(-phase, &sn, &cn, &sc_ok);
+                if (!sc_ok) sincosf(-phase, &sn, &cn);
                 // nco_out = cosf(-phase) + 1j*sinf(-phase)
                 const float nr = __fadd_rn(cn, __fsub_rn(__fmul_rn(0.0f, sn), 0.0f));
                 const float ni = __fadd_rn(0.0f, __fadd_rn(0.0f, sn));

@@ -110,29 +110,30 @@ struct UrhDemodParams {
     float max_mag;      // ASK normalisation (pyx:343-352)
 };
 
-template <int MOD>
-__device__ __forceinline__ float urh_demod_one(float pr, float pi, float re, float im, const UrhDemodParams& P) {
-    const float mag = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
-    if (mag <= P.noise_sqrd) return P.noise_value;
-    if (MOD == URH_MOD_ASK) {
-        return __fdiv_rn(__fsqrt_rn(mag), P.max_mag);
-    } else if (MOD == URH_MOD_FSK) {
-        // tmp = (a - 1j*b) * (c + 1j*d) evaluated exactly as the C++ std::complex<float> expression:
-        // 1j*v = (0*v - 1*0, 0*0 + 1*v); real -/+ complex acts on (real, 0).  Signed zeros matter.
-        const float tr = __fsub_rn(__fmul_rn(0.0f, pi), 0.0f);
-        const float ti = __fadd_rn(0.0f, pi);
-        const float A = __fsub_rn(pr, tr);
-        const float B = __fsub_rn(0.0f, ti);
-        const float ur = __fsub_rn(__fmul_rn(0.0f, im), 0.0f);
-        const float ui = __fadd_rn(0.0f, im);
-        const float C = __fadd_rn(re, ur);
-        const float D = __fadd_rn(0.0f, ui);
-        const float xr = __fsub_rn(__fmul_rn(A, C), __fmul_rn(B, D));
-        const float xi = __fadd_rn(__fmul_rn(A, D), __fmul_rn(B, C));
-        return urh_atan2f(xi, xr);
-    } else {
-        return 0.0f;
-    }
+// Per-sample terms of the reference's std::complex<float> expression
+//   tmp = (x[i-1].re - 1j*x[i-1].im) * (x[i].re + 1j*x[i].im)
+// with 1j*v = (0*v - 1*0, 0*0 + 1*v) and real -/+ complex acting on (real, 0); signed zeros matter.
+// For a sample (re, im):   zt = 0*im - 0
+//   as the CURRENT factor :  C = re + zt,  D = 0 + im
+//   as the PREVIOUS factor:  A = re - zt,  B = 0 - (0 + im) = 0 - D
+// so each sample's four terms are computed once and (A, B) travel to the next sample.
+struct UrhFskTerms {
+    float A, B, C, D;
+};
+__device__ __forceinline__ UrhFskTerms urh_fsk_terms(float re, float im) {
+    UrhFskTerms t;
+    const float zt = __fsub_rn(__fmul_rn(0.0f, im), 0.0f);
+    t.C = __fadd_rn(re, zt);
+    t.A = __fsub_rn(re, zt);
+    t.D = __fadd_rn(0.0f, im);
+    t.B = __fsub_rn(0.0f, t.D);
+    return t;
+}
+// atan2f(imag, real) of (A + iB)(C + iD), bit-faithful to signal_functions.pyx:375-376
+__device__ __forceinline__ float urh_fsk_angle(float A, float B, float C, float D) {
+    const float xr = __fsub_rn(__fmul_rn(A, C), __fmul_rn(B, D));
+    const float xi = __fadd_rn(__fmul_rn(A, D), __fmul_rn(B, C));
+    return urh_atan2f_v2(xi, xr);
 }
 
 // ---- classification (signal_functions.pyx:435-442) --------------------------------------------------

@@ -28,11 +28,12 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
     UrhRunTracker rt;
     if (DIGITIZE) rt.init(tol, staging + tile * (int64_t)stage_cap);
 
-    // FSK predecessor of the tile's first sample
-    float cr = 0.0f, ci = 0.0f;
+    // FSK: (A, B) terms of the sample preceding the tile's first sample
+    float cA = 0.0f, cB = 0.0f;
     if (MOD == URH_MOD_FSK && tile_start > 0 && lane == 0) {
         const UrhPair pv = urh_load_pair<DT>(iq, tile_start - 1, n, false);
-        cr = pv.r0; ci = pv.i0;
+        const UrhFskTerms t = urh_fsk_terms(pv.r0, pv.i0);
+        cA = t.A; cB = t.B;
     }
 
     UrhPair cur = urh_load_pair<DT>(iq, tile_start + 2 * lane, n, vec_in != 0);
@@ -41,16 +42,24 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
         UrhPair nxt;
         if (it + 1 < iters) nxt = urh_load_pair<DT>(iq, pos0 + 64, n, vec_in != 0);
 
-        float pr = 0.0f, pi = 0.0f;
+        // noise gate: magnitude = re*re + im*im <= noise_sqrd (pyx:366-369)
+        const float m0 = __fadd_rn(__fmul_rn(cur.r0, cur.r0), __fmul_rn(cur.i0, cur.i0));
+        const float m1 = __fadd_rn(__fmul_rn(cur.r1, cur.r1), __fmul_rn(cur.i1, cur.i1));
+        float s0 = dp.noise_value, s1 = dp.noise_value;
         if (MOD == URH_MOD_FSK) {
-            pr = __shfl_up_sync(URH_FULL_MASK, cur.r1, 1);
-            pi = __shfl_up_sync(URH_FULL_MASK, cur.i1, 1);
-            if (lane == 0) { pr = cr; pi = ci; }
-            cr = __shfl_sync(URH_FULL_MASK, cur.r1, 31);
-            ci = __shfl_sync(URH_FULL_MASK, cur.i1, 31);
+            const UrhFskTerms t0 = urh_fsk_terms(cur.r0, cur.i0);
+            const UrhFskTerms t1 = urh_fsk_terms(cur.r1, cur.i1);
+            float pA = __shfl_up_sync(URH_FULL_MASK, t1.A, 1);
+            float pB = __shfl_up_sync(URH_FULL_MASK, t1.B, 1);
+            if (lane == 0) { pA = cA; pB = cB; }
+            cA = __shfl_sync(URH_FULL_MASK, t1.A, 31);
+            cB = __shfl_sync(URH_FULL_MASK, t1.B, 31);
+            if (!(m0 <= dp.noise_sqrd)) s0 = urh_fsk_angle(pA, pB, t0.C, t0.D);
+            if (!(m1 <= dp.noise_sqrd)) s1 = urh_fsk_angle(t0.A, t0.B, t1.C, t1.D);
+        } else if (MOD == URH_MOD_ASK) {
+            if (!(m0 <= dp.noise_sqrd)) s0 = __fdiv_rn(__fsqrt_rn(m0), dp.max_mag);
+            if (!(m1 <= dp.noise_sqrd)) s1 = __fdiv_rn(__fsqrt_rn(m1), dp.max_mag);
         }
-        float s0 = urh_demod_one<MOD>(pr, pi, cur.r0, cur.i0, dp);
-        const float s1 = urh_demod_one<MOD>(cur.r0, cur.i0, cur.r1, cur.i1, dp);
         if (pos0 == 0) s0 = dp.noise_value;  // result[0] = NOISE (pyx:361)
 
         const bool v0 = pos0 < n, v1 = pos0 + 1 < n;

@@ -171,3 +171,55 @@ URH_HD float urh_atan2f(float y, float x) {
         default: return URH_SUB(URH_SUB(z, URH_PI_LO), URH_PI);
     }
 }
+
+// ---- branch-light formulation (same results, fewer instructions on the GPU) -------------------------
+// urh_atan2f_v2(y, x) == urh_atan2f(y, x) bit-for-bit (checked on the CPU by
+// tests/test_atan2f_restatement.py against libm).  Differences in structure only:
+//  * the zero / one / exponent-gap special cases of e_atan2f.c are folded into the general path where
+//    the general path provably yields the same float (y == +-0 with x != 0, x == 1, |k| > 60);
+//    only x == +-0 and non-finite operands take the literal reference path;
+//  * |y/x| < 0.4375 (every narrow-band FSK sample) needs no second division and no table;
+//  * the four reduction intervals share one num/den/poly evaluation through selected constants:
+//    num = fl(fl(a*q) + b), den = fl(fl(c*q) + d) reproduces (2q-1)/(2+q), (q-1)/(q+1),
+//    (q-1.5)/(1+1.5q) and -1/q with the reference's roundings (a*q is exact for a in {0,1,2}).
+URH_HD float urh_atan2f_v2(float y, float x) {
+    const int32_t hx = URH_F2I(x), hy = URH_F2I(y);
+    const int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+    if (((uint32_t)(ix - 1) >= 0x7f7fffffu) | (iy >= 0x7f800000)) return urh_atan2f(y, x);
+    const float q = URH_DIV(URH_I2F(iy), URH_I2F(ix));
+    const int32_t iq = URH_F2I(q);
+    float z;
+    if (iq < 0x3ee00000) {
+        const float z2 = URH_MUL(q, q);
+        const float w = URH_MUL(z2, z2);
+        const float s1 = URH_MUL(z2, URH_ADD(URH_AT0, URH_MUL(w, URH_ADD(URH_AT2, URH_MUL(w, URH_ADD(URH_AT4,
+                          URH_MUL(w, URH_ADD(URH_AT6, URH_MUL(w, URH_ADD(URH_AT8, URH_MUL(w, URH_AT10)))))))))));
+        const float s2 = URH_MUL(w, URH_ADD(URH_AT1, URH_MUL(w, URH_ADD(URH_AT3, URH_MUL(w, URH_ADD(URH_AT5,
+                          URH_MUL(w, URH_ADD(URH_AT7, URH_MUL(w, URH_AT9)))))))));
+        z = URH_SUB(q, URH_MUL(q, URH_ADD(s1, s2)));
+    } else if (iq >= 0x4c000000) {
+        z = URH_ADD(URH_ATANHI3, URH_ATANLO3);
+    } else {
+        float a, b, c, d, hi, lo;
+        if (iq < 0x3f980000) {
+            if (iq < 0x3f300000) { a = 2.0f; b = -1.0f; c = 1.0f; d = 2.0f; hi = URH_ATANHI0; lo = URH_ATANLO0; }
+            else { a = 1.0f; b = -1.0f; c = 1.0f; d = 1.0f; hi = URH_ATANHI1; lo = URH_ATANLO1; }
+        } else {
+            if (iq < 0x401c0000) { a = 1.0f; b = -1.5f; c = 1.5f; d = 1.0f; hi = URH_ATANHI2; lo = URH_ATANLO2; }
+            else { a = 0.0f; b = -1.0f; c = 1.0f; d = 0.0f; hi = URH_ATANHI3; lo = URH_ATANLO3; }
+        }
+        const float num = URH_ADD(URH_MUL(a, q), b);
+        const float den = URH_ADD(URH_MUL(c, q), d);
+        const float xr = URH_DIV(num, den);
+        const float z2 = URH_MUL(xr, xr);
+        const float w = URH_MUL(z2, z2);
+        const float s1 = URH_MUL(z2, URH_ADD(URH_AT0, URH_MUL(w, URH_ADD(URH_AT2, URH_MUL(w, URH_ADD(URH_AT4,
+                          URH_MUL(w, URH_ADD(URH_AT6, URH_MUL(w, URH_ADD(URH_AT8, URH_MUL(w, URH_AT10)))))))))));
+        const float s2 = URH_MUL(w, URH_ADD(URH_AT1, URH_MUL(w, URH_ADD(URH_AT3, URH_MUL(w, URH_ADD(URH_AT5,
+                          URH_MUL(w, URH_ADD(URH_AT7, URH_MUL(w, URH_AT9)))))))));
+        z = URH_SUB(hi, URH_SUB(URH_SUB(URH_MUL(xr, URH_ADD(s1, s2)), lo), xr));
+    }
+    float r = z;
+    if (hx < 0) r = URH_SUB(URH_PI, URH_SUB(z, URH_PI_LO));
+    return (hy < 0) ? URH_I2F(URH_F2I(r) ^ (int32_t)0x80000000) : r;
+}
