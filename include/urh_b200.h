@@ -91,6 +91,8 @@ int urh_pulses_device_ptr(urh_ctx* ctx, const int64_t** d_rows, int64_t* k);
 /* CUDA-event timing of the dominant (dense, sample-rate) kernel of the last demod/digitize call */
 int urh_set_profiling(urh_ctx* ctx, int enabled);
 int urh_last_dense_ms(urh_ctx* ctx, float* ms);
+/* packed (f32x2) division used by the FSK fast path vs __fdiv_rn on `count` random operand pairs */
+int urh_selftest_packed_div(urh_ctx* ctx, uint64_t seed, int64_t count, int64_t* mismatches, int64_t* tested);
 /* synthetic phase-continuous 2-FSK bursts + AWGN + noise-only gaps generated in HBM (SURVEY 8d recipe) */
 int urh_synth_fsk(urh_ctx* ctx, float* d_iq, int64_t n, int64_t global_offset, int sps, const int8_t* d_sym_bit,
                   const int32_t* d_sym_sum, double dev_ratio, float amplitude, float sigma, uint64_t seed,

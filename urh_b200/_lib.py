@@ -80,6 +80,7 @@ SIGNATURES = {
     "urh_pulses_device_ptr": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
     "urh_set_profiling": (i32, [vp, i32]),
     "urh_last_dense_ms": (i32, [vp, C.POINTER(f32)]),
+    "urh_selftest_packed_div": (i32, [vp, C.c_uint64, i64, C.POINTER(i64), C.POINTER(i64)]),
     "urh_synth_fsk": (i32, [vp, vp, i64, i64, i32, vp, vp, C.c_double, f32, f32, C.c_uint64, i64, i64, i64, i64, i64]),
 }
 

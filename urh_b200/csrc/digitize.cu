@@ -5,6 +5,7 @@
 #include "dense.cuh"
 #include "scan.cuh"
 #include "sparse.cuh"
+#include "fsk_fast.cuh"
 
 #include <math.h>
 
@@ -27,6 +28,14 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
 
     UrhRunTracker rt;
     if (DIGITIZE) rt.init(tol, staging + tile * (int64_t)stage_cap);
+
+    // full, aligned FSK tiles (all but possibly the last one): packed-f32x2 fast path, same bits
+    if (MOD == URH_MOD_FSK && tile_len == URH_TILE && vec_in && (!qad_out || vec_out) && (!DIGITIZE || cls.order == 2)) {
+        urh_fsk_full_tile<DT, DIGITIZE>(iq, n, tile_start, dp, qad_out, cls.thr[0], cls.noise_value, rt, init_cls,
+                                        cls_of_zero, lane);
+        if (DIGITIZE) rt.finish(tile_len, tiles + tile, lane);
+        return;
+    }
 
     // FSK: (A, B) terms of the sample preceding the tile's first sample
     float cA = 0.0f, cB = 0.0f;
@@ -341,5 +350,51 @@ extern "C" int urh_fetch_pulses(urh_ctx* ctx, int64_t* h_rows, int64_t k) {
 extern "C" int urh_pulses_device_ptr(urh_ctx* ctx, const int64_t** d_rows, int64_t* k) {
     if (d_rows) *d_rows = ctx->pulses;
     if (k) *k = ctx->pulses_k;
+    return URH_OK;
+}
+
+
+// ---- diagnostic: packed-division self test (tests/test_gpu_packed_div.py) ---------------------------
+__global__ void k_selftest_div(uint64_t seed, int64_t count, unsigned long long* mismatches, unsigned long long* tested) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0, ok = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        uint64_t h = seed + (uint64_t)i * 0x9E3779B97F4A7C15ull;
+        h = (h ^ (h >> 30)) * 0xBF58476D1CE4E5B9ull;
+        h = (h ^ (h >> 27)) * 0x94D049BB133111EBull;
+        h ^= h >> 31;
+        uint64_t g = h * 0xD6E8FEB86659FD93ull + 0x632BE59BD9B4E019ull;
+        g ^= g >> 29;
+        // exponents uniformly inside the window [27, 228), random mantissas; a few structured cases
+        uint32_t ea = 27 + (uint32_t)((h >> 40) % 201), eb = 27 + (uint32_t)((g >> 40) % 201);
+        uint32_t ma = (uint32_t)h & 0x7fffff, mb = (uint32_t)g & 0x7fffff;
+        if ((i & 15) == 1) ma = 0;
+        if ((i & 15) == 2) mb = 0;
+        if ((i & 15) == 3) { ma = 0x7fffff; }
+        if ((i & 15) == 4) { mb = 0x7fffff; }
+        if ((i & 15) == 5) { eb = ea; }
+        float a0 = __uint_as_float((ea << 23) | ma), b0 = __uint_as_float((eb << 23) | mb);
+        float a1 = __uint_as_float(((27 + (uint32_t)((g >> 12) % 201)) << 23) | (uint32_t)(h >> 9) & 0x7fffff);
+        float b1 = __uint_as_float(((27 + (uint32_t)((h >> 12) % 201)) << 23) | (uint32_t)(g >> 9) & 0x7fffff);
+        if ((i & 63) == 7) a1 = 0.0f;
+        const float2 q = urh_div2_window(make_float2(a0, a1), make_float2(b0, b1));
+        const float r0 = __fdiv_rn(a0, b0), r1 = __fdiv_rn(a1, b1);
+        bad += (__float_as_uint(q.x) != __float_as_uint(r0)) + (__float_as_uint(q.y) != __float_as_uint(r1));
+        ok += 2;
+    }
+    atomicAdd(mismatches, bad);
+    atomicAdd(tested, ok);
+}
+
+extern "C" int urh_selftest_packed_div(urh_ctx* ctx, uint64_t seed, int64_t count, int64_t* mismatches, int64_t* tested) {
+    urh_arena_reset(ctx);
+    unsigned long long* d;
+    URH_CHECK(urh_arena(ctx, 2, &d));
+    URH_CUDA(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
+    URH_LAUNCH(ctx, k_selftest_div, (unsigned)(ctx->sm_count * 8), 256, 0, seed, count, d, d + 1);
+    int64_t h[2];
+    URH_CHECK(urh_read_i64(ctx, (const int64_t*)d, 2, h));
+    *mismatches = h[0];
+    *tested = h[1];
     return URH_OK;
 }
