@@ -108,6 +108,7 @@ struct UrhDemodParams {
     float noise_sqrd;   // noise_mag * noise_mag (float)
     float noise_value;  // NOISE sentinel
     float max_mag;      // ASK normalisation (pyx:343-352)
+    float one, mone;    // +1.0f / -1.0f as run-time values (see fsk_fast.cuh: keeps ptxas from contracting)
 };
 
 // Per-sample terms of the reference's std::complex<float> expression

@@ -31,8 +31,11 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
 
     // full, aligned FSK tiles (all but possibly the last one): packed-f32x2 fast path, same bits
     if (MOD == URH_MOD_FSK && tile_len == URH_TILE && vec_in && (!qad_out || vec_out) && (!DIGITIZE || cls.order == 2)) {
+        UrhOne one;
+        one.p = dp.one;
+        one.m = dp.mone;
         urh_fsk_full_tile<DT, DIGITIZE>(iq, n, tile_start, dp, qad_out, cls.thr[0], cls.noise_value, rt, init_cls,
-                                        cls_of_zero, lane);
+                                        cls_of_zero, lane, one);
         if (DIGITIZE) rt.finish(tile_len, tiles + tile, lane);
         return;
     }
@@ -229,6 +232,8 @@ static UrhDemodParams make_demod_params(float noise_mag, int mod_type, int dtype
     dp.noise_sqrd = sq;
     dp.noise_value = urh_noise_value(mod_type);
     dp.max_mag = max_magnitude_for(dtype);
+    dp.one = 1.0f;
+    dp.mone = -1.0f;
     return dp;
 }
 
