@@ -370,8 +370,9 @@ __global__ void k_selftest_div(uint64_t seed, int64_t count, unsigned long long*
         h ^= h >> 31;
         uint64_t g = h * 0xD6E8FEB86659FD93ull + 0x632BE59BD9B4E019ull;
         g ^= g >> 29;
-        // exponents uniformly inside the window [27, 228), random mantissas; a few structured cases
-        uint32_t ea = 27 + (uint32_t)((h >> 40) % 201), eb = 27 + (uint32_t)((g >> 40) % 201);
+        // exponents uniformly inside the window, random mantissas; a few structured cases
+        const uint32_t span = URH_DIVWIN_HI - URH_DIVWIN_LO;
+        uint32_t ea = URH_DIVWIN_LO + (uint32_t)((h >> 40) % span), eb = URH_DIVWIN_LO + (uint32_t)((g >> 40) % span);
         uint32_t ma = (uint32_t)h & 0x7fffff, mb = (uint32_t)g & 0x7fffff;
         if ((i & 15) == 1) ma = 0;
         if ((i & 15) == 2) mb = 0;
@@ -379,8 +380,10 @@ __global__ void k_selftest_div(uint64_t seed, int64_t count, unsigned long long*
         if ((i & 15) == 4) { mb = 0x7fffff; }
         if ((i & 15) == 5) { eb = ea; }
         float a0 = __uint_as_float((ea << 23) | ma), b0 = __uint_as_float((eb << 23) | mb);
-        float a1 = __uint_as_float(((27 + (uint32_t)((g >> 12) % 201)) << 23) | (uint32_t)(h >> 9) & 0x7fffff);
-        float b1 = __uint_as_float(((27 + (uint32_t)((h >> 12) % 201)) << 23) | (uint32_t)(g >> 9) & 0x7fffff);
+        float a1 = __uint_as_float(((URH_DIVWIN_LO + (uint32_t)((g >> 12) % span)) << 23) | ((uint32_t)(h >> 9) & 0x7fffff));
+        float b1 = __uint_as_float(((URH_DIVWIN_LO + (uint32_t)((h >> 12) % span)) << 23) | ((uint32_t)(g >> 9) & 0x7fffff));
+        if ((i & 15) == 6) { a1 = __uint_as_float((URH_DIVWIN_LO << 23)); b1 = __uint_as_float(((URH_DIVWIN_HI - 1) << 23) | 0x7fffff); }
+        if ((i & 15) == 8) { b1 = __uint_as_float((URH_DIVWIN_LO << 23)); a1 = __uint_as_float(((URH_DIVWIN_HI - 1) << 23) | 0x7fffff); }
         if ((i & 63) == 7) a1 = 0.0f;
         const float2 q = urh_div2_window(make_float2(a0, a1), make_float2(b0, b1));
         const float r0 = __fdiv_rn(a0, b0), r1 = __fdiv_rn(a1, b1);
