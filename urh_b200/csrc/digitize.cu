@@ -29,13 +29,14 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
     UrhRunTracker rt;
     if (DIGITIZE) rt.init(tol, staging + tile * (int64_t)stage_cap);
 
-    // full, aligned FSK tiles (all but possibly the last one): packed-f32x2 fast path, same bits
-    if (MOD == URH_MOD_FSK && tile_len == URH_TILE && vec_in && (!qad_out || vec_out) && (!DIGITIZE || cls.order == 2)) {
+    // full, aligned FSK tiles (all but the first and possibly the last one): packed-f32x2 fast path, same bits
+    if (MOD == URH_MOD_FSK && tile_len == URH_TILE && tile_start > 0 && vec_in && (!qad_out || vec_out) &&
+        (!DIGITIZE || cls.order == 2)) {
         UrhOne one;
         one.p = dp.one;
         one.m = dp.mone;
-        urh_fsk_full_tile<DT, DIGITIZE>(iq, n, tile_start, dp, qad_out, cls.thr[0], cls.noise_value, rt, init_cls,
-                                        cls_of_zero, lane, one);
+        if (qad_out) urh_fsk_full_tile<DT, DIGITIZE, true>(iq, n, tile_start, dp, qad_out, cls.thr[0], cls.noise_value, rt, lane, one);
+        else urh_fsk_full_tile<DT, DIGITIZE, false>(iq, n, tile_start, dp, qad_out, cls.thr[0], cls.noise_value, rt, lane, one);
         if (DIGITIZE) rt.finish(tile_len, tiles + tile, lane);
         return;
     }
