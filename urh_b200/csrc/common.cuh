@@ -101,7 +101,7 @@ int urh_ensure_stage(urh_ctx* ctx, size_t bytes);
 // read back `count` int64 scalars from device (synchronises the ctx stream)
 int urh_read_i64(urh_ctx* ctx, const int64_t* d_src, int count, int64_t* h_out);
 
-static inline int64_t urh_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ static inline int64_t urh_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // sample size in bytes of one IQ pair for dtype
 static inline int urh_iq_bytes(int dtype) {

@@ -183,12 +183,20 @@ struct UrhRunTracker {
         const uint32_t m0 = __ballot_sync(URH_FULL_MASK, b0);
         const uint32_t m1 = __ballot_sync(URH_FULL_MASK, b1);
         if ((m0 | m1) == 0u) return;
-        uint64_t bits = urh_spread_bits(m0) | (urh_spread_bits(m1) << 1);
-        while (bits) {
-            const int bit = __ffsll((long long)bits) - 1;
-            bits &= bits - 1;
-            const int p = it * 64 + bit;
-            const int cls_p = __shfl_sync(URH_FULL_MASK, (bit & 1) ? c1 : c0, bit >> 1);
+        walk(it, m0, m1, c0, c1, lane);
+    }
+    // Same as feed() but with the boundary predicates supplied by the caller (fsk_fast.cuh derives them
+    // without materialising class integers for the compare).
+    __device__ __forceinline__ void walk(int it, uint32_t m0, uint32_t m1, int c0, int c1, int lane) {
+        // merge the two boundary masks in sample order: sample 2l (mask m0) precedes sample 2l+1 (mask m1)
+        while (m0 | m1) {
+            const int l0 = m0 ? (__ffs(m0) - 1) : 64;
+            const int l1 = m1 ? (__ffs(m1) - 1) : 64;
+            const bool take0 = l0 <= l1;
+            const int l = take0 ? l0 : l1;
+            if (take0) m0 &= m0 - 1; else m1 &= m1 - 1;
+            const int p = it * 64 + 2 * l + (take0 ? 0 : 1);
+            const int cls_p = __shfl_sync(URH_FULL_MASK, take0 ? c0 : c1, l);
             if (run_cls == -2) {
                 first_cls = cls_p;                    // the forced boundary at p == 0 opens the head run
             } else if (is_head) {

@@ -1,0 +1,63 @@
+// Dense pass over an array of already-computed real samples (float32 / float64): classification + run
+// tracking only.  Used by grab_pulse_lens (stand-alone), segment_messages_from_magnitudes and
+// get_plateau_lengths.
+#pragma once
+#include "dense.cuh"
+
+// Classifier sources for the stand-alone digitizer / segmenter: float32 samples already in memory.
+struct SrcQad {  // grab_pulse_lens on a demodulated array
+    template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C) { return urh_classify((float)s, C); }
+};
+struct SrcAbove {  // segment_messages_from_magnitudes: class 1 = above noise (auto_interpretation.pyx:79)
+    template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C) { return (s > (T)C.thr[0]) ? 1 : 0; }
+};
+struct SrcCenter {  // get_plateau_lengths: -1/1 around center (auto_interpretation.pyx:183,197) as 0/1
+    template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C) { return (s <= (T)C.thr[0]) ? 0 : 1; }
+};
+
+template <typename T> struct UrhVec2;
+template <> struct UrhVec2<float> { typedef float2 type; };
+template <> struct UrhVec2<double> { typedef double2 type; };
+
+template <typename SRC, typename T>
+__global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32)
+k_dense_f32(const T* __restrict__ x, int64_t n, int vec_in, const __grid_constant__ UrhClassify cls, int tol,
+            UrhTileSummary* __restrict__ tiles, uint32_t* __restrict__ staging, int stage_cap,
+            int16_t* __restrict__ init_cls, int cls_of_zero) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * URH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int64_t tile_start = tile * URH_TILE;
+    if (tile_start >= n) return;
+    const int tile_len = (int)((n - tile_start) < URH_TILE ? (n - tile_start) : URH_TILE);
+    const int iters = (tile_len + 63) >> 6;
+    UrhRunTracker rt;
+    rt.init(tol, staging + tile * (int64_t)stage_cap);
+    // two 64-groups in flight per warp step
+    for (int it = 0; it < iters; it += 2) {
+        T a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+        const int64_t pa = tile_start + (int64_t)it * 64 + 2 * lane;
+        const int64_t pb = pa + 64;
+        if (vec_in && pa + 1 < n) {
+            const typename UrhVec2<T>::type v = __ldg((const typename UrhVec2<T>::type*)(x + pa));
+            a0 = v.x; a1 = v.y;
+        } else {
+            if (pa < n) a0 = __ldg(x + pa);
+            if (pa + 1 < n) a1 = __ldg(x + pa + 1);
+        }
+        const bool has_b = it + 1 < iters;
+        if (has_b) {
+            if (vec_in && pb + 1 < n) {
+                const typename UrhVec2<T>::type v = __ldg((const typename UrhVec2<T>::type*)(x + pb));
+                b0 = v.x; b1 = v.y;
+            } else {
+                if (pb < n) b0 = __ldg(x + pb);
+                if (pb + 1 < n) b1 = __ldg(x + pb + 1);
+            }
+        }
+        if (pa == 0 && init_cls) *init_cls = (int16_t)(((float)a0 == cls.noise_value) ? -1 : cls_of_zero);
+        rt.feed(it, SRC::template cls<T>(a0, cls), SRC::template cls<T>(a1, cls), pa < n, pa + 1 < n, lane);
+        if (has_b) rt.feed(it + 1, SRC::template cls<T>(b0, cls), SRC::template cls<T>(b1, cls), pb < n, pb + 1 < n, lane);
+    }
+    rt.finish(tile_len, tiles + tile, lane);
+}
+

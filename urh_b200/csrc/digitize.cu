@@ -6,6 +6,7 @@
 #include "scan.cuh"
 #include "sparse.cuh"
 #include "fsk_fast.cuh"
+#include "dense_f32.cuh"
 
 #include <math.h>
 
@@ -91,59 +92,6 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
         cur = nxt;
     }
     if (DIGITIZE) rt.finish(tile_len, tiles + tile, lane);
-}
-
-// Classifier sources for the stand-alone digitizer / segmenter: float32 samples already in memory.
-struct SrcQad {  // grab_pulse_lens on a demodulated array
-    __device__ __forceinline__ static int cls(float s, const UrhClassify& C) { return urh_classify(s, C); }
-};
-struct SrcAbove {  // segment_messages_from_magnitudes: class 1 = above noise (auto_interpretation.pyx:79)
-    __device__ __forceinline__ static int cls(float s, const UrhClassify& C) { return (s > C.thr[0]) ? 1 : 0; }
-};
-struct SrcCenter {  // get_plateau_lengths: -1/1 around center (auto_interpretation.pyx:183,197) as 0/1
-    __device__ __forceinline__ static int cls(float s, const UrhClassify& C) { return (s <= C.thr[0]) ? 0 : 1; }
-};
-
-template <typename SRC>
-__global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32)
-k_dense_f32(const float* __restrict__ x, int64_t n, int vec_in, const __grid_constant__ UrhClassify cls, int tol,
-            UrhTileSummary* __restrict__ tiles, uint32_t* __restrict__ staging, int stage_cap,
-            int16_t* __restrict__ init_cls, int cls_of_zero) {
-    const int lane = threadIdx.x & 31;
-    const int64_t tile = (int64_t)blockIdx.x * URH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    const int64_t tile_start = tile * URH_TILE;
-    if (tile_start >= n) return;
-    const int tile_len = (int)((n - tile_start) < URH_TILE ? (n - tile_start) : URH_TILE);
-    const int iters = (tile_len + 63) >> 6;
-    UrhRunTracker rt;
-    rt.init(tol, staging + tile * (int64_t)stage_cap);
-    // two 64-groups in flight per warp step
-    for (int it = 0; it < iters; it += 2) {
-        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-        const int64_t pa = tile_start + (int64_t)it * 64 + 2 * lane;
-        const int64_t pb = pa + 64;
-        if (vec_in && pa + 1 < n) {
-            const float2 v = __ldg((const float2*)(x + pa));
-            a0 = v.x; a1 = v.y;
-        } else {
-            if (pa < n) a0 = __ldg(x + pa);
-            if (pa + 1 < n) a1 = __ldg(x + pa + 1);
-        }
-        const bool has_b = it + 1 < iters;
-        if (has_b) {
-            if (vec_in && pb + 1 < n) {
-                const float2 v = __ldg((const float2*)(x + pb));
-                b0 = v.x; b1 = v.y;
-            } else {
-                if (pb < n) b0 = __ldg(x + pb);
-                if (pb + 1 < n) b1 = __ldg(x + pb + 1);
-            }
-        }
-        if (pa == 0 && init_cls) *init_cls = (int16_t)((a0 == cls.noise_value) ? -1 : cls_of_zero);
-        rt.feed(it, SRC::cls(a0, cls), SRC::cls(a1, cls), pa < n, pa + 1 < n, lane);
-        if (has_b) rt.feed(it + 1, SRC::cls(b0, cls), SRC::cls(b1, cls), pb < n, pb + 1 < n, lane);
-    }
-    rt.finish(tile_len, tiles + tile, lane);
 }
 
 // =====================================================================================================
@@ -295,7 +243,7 @@ extern "C" int urh_grab_pulse_lens(urh_ctx* ctx, const float* d_qad, int64_t n, 
     const unsigned grid = (unsigned)urh_div_up(ntiles, URH_WARPS_PER_BLOCK);
     const int vec_in = (((uintptr_t)d_qad % 8) == 0) ? 1 : 0;
     URH_PROF_BEGIN(ctx);
-    URH_LAUNCH(ctx, (k_dense_f32<SrcQad>), grid, URH_WARPS_PER_BLOCK * 32, 0, d_qad, n, vec_in, cls, tol, tiles,
+    URH_LAUNCH(ctx, (k_dense_f32<SrcQad, float>), grid, URH_WARPS_PER_BLOCK * 32, 0, d_qad, n, vec_in, cls, tol, tiles,
                staging, cap, d_init, host_classify(0.0f, cls));
     URH_PROF_END(ctx);
     return digitize_finish(ctx, n, tol, mod_type == URH_MOD_ASK, samples_per_symbol, tiles, staging, cap, d_init, k);

@@ -97,11 +97,21 @@ int urh_collect_candidates(urh_ctx* ctx, int64_t n, int tol, const UrhTileSummar
     ident.len = 0;
     ident.cls = 0;
     ident.flags = 2 | 1;
-    URH_CHECK((urhscan::device_scan<RunCarry, RunCarryOp>(ctx, carry, ntiles, RunCarryOp(), ident, true, nullptr)));
+    RunCarry* d_total_run;
+    URH_CHECK(urh_arena(ctx, 2, &d_total_run));
+    URH_CHECK((urhscan::device_scan<RunCarry, RunCarryOp>(ctx, carry, ntiles, RunCarryOp(), ident, true, d_total_run)));
     URH_LAUNCH(ctx, k_tile_heads, g, 256, 0, tiles, carry, ntiles, tol, head_rel, total);
     URH_CHECK((urhscan::device_scan<int64_t, urhscan::AddI64>(ctx, total, ntiles, urhscan::AddI64(), (int64_t)0, true, d_count)));
     int64_t C = 0;
     URH_CHECK(urh_read_i64(ctx, d_count, 1, &C));
+    {
+        int64_t raw[2];
+        URH_CHECK(urh_read_i64(ctx, (const int64_t*)d_total_run, 2, raw));
+        RunCarry tr;
+        memcpy(&tr, raw, sizeof(tr));
+        out->last_cls = tr.cls;
+        out->last_len = tr.len;
+    }
     out->count = C;
     out->pos = nullptr;
     out->cls = nullptr;

@@ -7,6 +7,9 @@ struct UrhCandidates {
     int64_t count;   // number of candidates (host copy)
     int64_t* pos;    // device: absolute sample index run_start + tolerance
     int16_t* cls;    // device: class of the run
+    // the run that contains the LAST sample of the stream (host copies): class and length
+    int32_t last_cls;
+    int64_t last_len;
 };
 
 // Stitch runs across tile edges (scan over the tile table), add the per-tile head candidates and gather
