@@ -87,6 +87,32 @@ int urh_demod_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, flo
 int urh_fetch_pulses(urh_ctx* ctx, int64_t* h_rows, int64_t k);          /* D2H of the last result   */
 int urh_pulses_device_ptr(urh_ctx* ctx, const int64_t** d_rows, int64_t* k);
 
+/* ---- auto-interpretation statistics (stats.cu) ------------------------------------------------------- */
+/* replaces util.get_magnitudes (util.pyx:128-136): float64[n] */
+int urh_get_magnitudes(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, double* d_out);
+/* per-chunk (sum, max) of the magnitudes, chunks counted from the END of the capture as
+ * AutoInterpretation.detect_noise_level does (AutoInterpretation.py:60-91); h_sum/h_max: host arrays [nchunks] */
+int urh_noise_chunk_stats_iq(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int64_t chunksize, int nchunks,
+                             double* h_sum, double* h_max);
+int urh_noise_chunk_stats(urh_ctx* ctx, const void* d_mags, int is_f64, int64_t n, int64_t chunksize, int nchunks,
+                          double* h_sum, double* h_max);
+/* AutoInterpretation.detect_center (AutoInterpretation.py:226-277), sample-rate part:
+ * stats  -> h_out[7] = {#samples > -4, r0, r1 (rank window after the 5 %/95 % trim and max_size), min, max, mean, var}
+ * hist   -> counts of the rank-trimmed samples in the bins hmin + k*hstep, k = 0..nbins (np.histogram semantics) */
+int urh_center_stats(urh_ctx* ctx, const float* d_x, int64_t n, int64_t max_size, double* h_out);
+int urh_center_histogram(urh_ctx* ctx, const float* d_x, int64_t n, int64_t r0, int64_t r1, double hmin, double hstep,
+                         int64_t nbins, int64_t* h_hist);
+/* replaces auto_interpretation.segment_messages_from_magnitudes (auto_interpretation.pyx:55-111) */
+int urh_segment_messages(urh_ctx* ctx, const void* d_mags, int is_f64, int64_t n, float noise_threshold,
+                         int64_t* h_segments, int64_t cap, int64_t* k);
+/* replaces auto_interpretation.get_plateau_lengths (auto_interpretation.pyx:179-208) */
+int urh_plateau_lengths(urh_ctx* ctx, const float* d_rect, int64_t n, float center, int percentage, uint64_t* h_out,
+                        int64_t cap, int64_t* k);
+/* replaces auto_interpretation.median_filter (auto_interpretation.pyx:211-240); k <= 64 */
+int urh_median_filter(urh_ctx* ctx, const double* d_x, int64_t n, unsigned int k, float* d_out);
+/* replaces util.arr2decibel (util.pyx:38-48): count complex64 values -> float32 dB */
+int urh_arr2decibel(urh_ctx* ctx, const float* d_complex, int64_t count, float* d_out);
+
 /* ---- measurement utilities (not part of the reference's API surface) -------------------------------- */
 /* CUDA-event timing of the dominant (dense, sample-rate) kernel of the last demod/digitize call */
 int urh_set_profiling(urh_ctx* ctx, int enabled);

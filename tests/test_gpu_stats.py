@@ -1,0 +1,104 @@
+"""GPU parity: auto-interpretation statistics (stats.cu + urh_b200.ainterpretation) vs golden vectors / oracle."""
+import numpy as np
+import pytest
+
+from conftest import CAPTURES, bits_equal, load_golden, synth_fsk
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def AI():
+    from urh_b200.ainterpretation import AutoInterpretation
+
+    return AutoInterpretation
+
+
+@pytest.mark.parametrize("name", CAPTURES)
+def test_magnitudes_noise_segments_golden(AI, oracle, name):
+    from urh_b200.cythonext import util
+
+    g = load_golden("capture_" + name)
+    mags = util.get_magnitudes(g["iq"])
+    assert mags.dtype == np.float64
+    assert np.array_equal(mags, oracle.get_magnitudes(g["iq"]), equal_nan=True)
+    assert np.array_equal(mags[:64], g["mag_head"])
+    assert AI.detect_noise_level(mags) == float(g["auto_noise"])
+    assert AI.detect_noise_level_iq(g["iq"]) == float(g["auto_noise"])
+    seg = AI.segment_messages_from_magnitudes(mags, float(g["noise"]))
+    assert np.array_equal(np.array(seg, dtype=np.int64).reshape(-1, 2), g["segments"])
+    seg32 = AI.segment_messages_from_magnitudes(mags.astype(np.float32), float(g["noise"]))
+    assert seg32 == oracle.segment_messages_from_magnitudes(mags.astype(np.float32), float(g["noise"]))
+
+
+@pytest.mark.parametrize("name", CAPTURES)
+def test_detect_center_golden(AI, name):
+    g = load_golden("capture_" + name)
+    m = g["meta"]
+    c = AI.detect_center(g["qad_" + m["mod"]])
+    gc = float(g["detect_center"])
+    if np.isnan(gc):
+        assert c is None
+    else:
+        # variance accumulated in double on the GPU vs numpy's pairwise float32: bin edges move by
+        # ~1e-7 relative, so the center (mean of two bin edges) agrees to ~1e-6 of the signal scale
+        assert c is not None and abs(c - gc) <= 2e-6 * max(1.0, abs(gc)), (c, gc)
+
+
+def test_segmentation_randomised(AI, oracle):
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        n = int(rng.choice([1, 9, 10, 11, 100, 2047, 2048, 2049, 30000]))
+        period = int(rng.integers(5, 400))
+        env = np.repeat(rng.integers(0, 2, n // period + 1), period)[:n].astype(np.float64)
+        mags = env + 0.3 * rng.random(n)
+        flips = rng.random(n) < 0.03
+        mags[flips] = 1.3 - mags[flips]
+        for arr in (mags, mags.astype(np.float32)):
+            assert AI.segment_messages_from_magnitudes(arr, 0.65) == oracle.segment_messages_from_magnitudes(arr, 0.65), (trial, n)
+
+
+def test_plateaus_median_decibel(AI, oracle):
+    from urh_b200.cythonext import auto_interpretation as cai
+    from urh_b200.cythonext import util
+
+    rng = np.random.default_rng(5)
+    for n in (1, 7, 100, 5000, 70000):
+        period = int(rng.integers(3, 50))
+        x = (np.repeat(rng.standard_normal(n // period + 1), period)[:n] + 0.05 * rng.standard_normal(n)).astype(np.float32)
+        for pct in (25, 100, 3):
+            assert np.array_equal(cai.get_plateau_lengths(x, 0.1, pct), oracle.get_plateau_lengths(x, 0.1, pct)), (n, pct)
+        d = rng.standard_normal(n)
+        for k in (3, 11, 4):
+            assert np.array_equal(cai.median_filter(d, k), oracle.median_filter(d, k)), (n, k)
+    z = (rng.standard_normal((37, 64)) + 1j * rng.standard_normal((37, 64))).astype(np.complex64)
+    db = util.arr2decibel(z)
+    ref = oracle.arr2decibel(z)
+    assert db.shape == ref.shape and db.dtype == np.float32
+    assert np.max(np.abs(db - ref)) <= 1e-5  # CUDA log10f vs glibc log10f: <= 2 ulp
+
+
+def test_detect_center_large_vs_oracle(AI, oracle):
+    from urh_b200.cythonext import signal_functions as sf
+
+    iq = synth_fsk(400000, sps=100, seed=2, gap_every=50000)
+    qad = sf.afp_demod(iq, 0.05, "FSK", 2)
+    c = AI.detect_center(qad)
+    ref = oracle.detect_center(qad)
+    assert abs(c - ref) <= 2e-6
+    c2 = AI.detect_center(qad, max_size=50000)
+    assert abs(c2 - oracle.detect_center(qad, max_size=50000)) <= 2e-6
+
+
+def test_estimate_matches_golden(AI):
+    for name in ("fsk", "ask", "enocean", "homematic"):
+        g = load_golden("capture_" + name)
+        est = g["meta"]["estimate"]
+        res = AI.estimate(g["iq"])
+        assert (res is None) == (est is None)
+        if est is not None:
+            assert res["modulation_type"] == est["modulation_type"]
+            assert res["bit_length"] == est["bit_length"]
+            assert res["tolerance"] == est["tolerance"]
+            assert res["noise"] == est["noise"]
+            assert abs(res["center"] - est["center"]) <= 1e-5 * max(1.0, abs(est["center"]))

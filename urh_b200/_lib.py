@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liburh_b200.so")
+LIB_PATH = os.environ.get("URH_B200_LIB", os.path.join(HERE, "liburh_b200.so"))
 
 URH_OK = 0
 ERR_CUDA, ERR_INVALID, ERR_DTYPE, ERR_NOMEM, ERR_MODULATION, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
@@ -78,6 +78,15 @@ SIGNATURES = {
     "urh_demod_digitize": (i32, [vp, vp, i32, i64, f32, i32, f32, u16, u32, u8, f32, vp, C.POINTER(i64)]),
     "urh_fetch_pulses": (i32, [vp, vp, i64]),
     "urh_pulses_device_ptr": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]),
+    "urh_get_magnitudes": (i32, [vp, vp, i32, i64, vp]),
+    "urh_noise_chunk_stats_iq": (i32, [vp, vp, i32, i64, i64, i32, vp, vp]),
+    "urh_noise_chunk_stats": (i32, [vp, vp, i32, i64, i64, i32, vp, vp]),
+    "urh_center_stats": (i32, [vp, vp, i64, i64, vp]),
+    "urh_center_histogram": (i32, [vp, vp, i64, i64, i64, C.c_double, C.c_double, i64, vp]),
+    "urh_segment_messages": (i32, [vp, vp, i32, i64, f32, vp, i64, C.POINTER(i64)]),
+    "urh_plateau_lengths": (i32, [vp, vp, i64, f32, i32, vp, i64, C.POINTER(i64)]),
+    "urh_median_filter": (i32, [vp, vp, i64, C.c_uint, vp]),
+    "urh_arr2decibel": (i32, [vp, vp, i64, vp]),
     "urh_set_profiling": (i32, [vp, i32]),
     "urh_last_dense_ms": (i32, [vp, C.POINTER(f32)]),
     "urh_selftest_packed_div": (i32, [vp, C.c_uint64, i64, C.POINTER(i64), C.POINTER(i64)]),

@@ -48,6 +48,20 @@ def up_to_date():
         return fh.read().strip() == _digest()
 
 
+def build_variant(name, defines):
+    """experiment helper: build urh_b200/variants/liburh_b200_<name>.so with extra -D flags"""
+    vdir = os.path.join(HERE, "variants")
+    os.makedirs(os.path.join(vdir, "obj_" + name), exist_ok=True)
+    objs = []
+    for src in sources():
+        obj = os.path.join(vdir, "obj_" + name, os.path.basename(src)[:-3] + ".o")
+        subprocess.check_call([NVCC] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", src, "-o", obj])
+        objs.append(obj)
+    out = os.path.join(vdir, "liburh_b200_%s.so" % name)
+    subprocess.check_call([NVCC, "-shared", "-o", out] + objs + ["-ccbin", "/usr/bin/g++", "-lcufft", "-ldl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"])
+    return out
+
+
 def build(force=False, verbose=False):
     if up_to_date() and not force:
         return LIB

@@ -5,6 +5,9 @@
 #include "dense.cuh"
 #include "scan.cuh"
 #include "sparse.cuh"
+#ifndef URH_FAST_MIN_BLOCKS
+#define URH_FAST_MIN_BLOCKS 5
+#endif
 #include "fsk_fast.cuh"
 #include "dense_f32.cuh"
 
@@ -19,9 +22,12 @@ template <int DT, int MOD, bool DIGITIZE>
 __global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32)
 k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __restrict__ qad_out, int vec_in,
            int vec_out, const __grid_constant__ UrhClassify cls, int tol, UrhTileSummary* __restrict__ tiles,
-           uint32_t* __restrict__ staging, int stage_cap, int16_t* __restrict__ init_cls, int cls_of_zero) {
+           uint32_t* __restrict__ staging, int stage_cap, int16_t* __restrict__ init_cls, int cls_of_zero,
+           int64_t tile_begin, int64_t tile_count) {
     const int lane = threadIdx.x & 31;
-    const int64_t tile = (int64_t)blockIdx.x * URH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int64_t tile_rel = (int64_t)blockIdx.x * URH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (tile_rel >= tile_count) return;
+    const int64_t tile = tile_begin + tile_rel;
     const int64_t tile_start = tile * URH_TILE;
     if (tile_start >= n) return;
     const int tile_len = (int)((n - tile_start) < URH_TILE ? (n - tile_start) : URH_TILE);
@@ -29,18 +35,6 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
 
     UrhRunTracker rt;
     if (DIGITIZE) rt.init(tol, staging + tile * (int64_t)stage_cap);
-
-    // full, aligned FSK tiles (all but the first and possibly the last one): packed-f32x2 fast path, same bits
-    if (MOD == URH_MOD_FSK && tile_len == URH_TILE && tile_start > 0 && vec_in && (!qad_out || vec_out) &&
-        (!DIGITIZE || cls.order == 2)) {
-        UrhOne one;
-        one.p = dp.one;
-        one.m = dp.mone;
-        if (qad_out) urh_fsk_full_tile<DT, DIGITIZE, true>(iq, n, tile_start, dp, qad_out, cls.thr[0], cls.noise_value, rt, lane, one);
-        else urh_fsk_full_tile<DT, DIGITIZE, false>(iq, n, tile_start, dp, qad_out, cls.thr[0], cls.noise_value, rt, lane, one);
-        if (DIGITIZE) rt.finish(tile_len, tiles + tile, lane);
-        return;
-    }
 
     // FSK: (A, B) terms of the sample preceding the tile's first sample
     float cA = 0.0f, cB = 0.0f;
@@ -92,6 +86,26 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
         cur = nxt;
     }
     if (DIGITIZE) rt.finish(tile_len, tiles + tile, lane);
+}
+
+// Fast kernel: full, aligned, order-2 FSK tiles [tile_begin, tile_begin + tile_count), tile_begin >= 1
+// (fsk_fast.cuh: packed f32x2 math, same bits as the generic kernel).
+template <int DT, bool DIGITIZE, bool WRITE>
+__global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32, URH_FAST_MIN_BLOCKS)
+k_fsk_fast(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __restrict__ qad_out, float thr0,
+           float cls_noise, int tol, UrhTileSummary* __restrict__ tiles, uint32_t* __restrict__ staging, int stage_cap,
+           int64_t tile_begin, int64_t tile_count) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile_rel = (int64_t)blockIdx.x * URH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (tile_rel >= tile_count) return;
+    const int64_t tile = tile_begin + tile_rel;
+    UrhRunTracker rt;
+    if (DIGITIZE) rt.init(tol, staging + tile * (int64_t)stage_cap);
+    UrhOne one;
+    one.p = dp.one;
+    one.m = dp.mone;
+    urh_fsk_full_tile<DT, DIGITIZE, WRITE>(iq, n, tile * URH_TILE, dp, qad_out, thr0, cls_noise, rt, lane, one);
+    if (DIGITIZE) rt.finish(URH_TILE, tiles + tile, lane);
 }
 
 // =====================================================================================================
@@ -147,12 +161,32 @@ static int launch_dense_iq_t(urh_ctx* ctx, const void* d_iq, int64_t n, const Ur
                              const UrhClassify& cls, int tol, UrhTileSummary* tiles, uint32_t* staging,
                              int stage_cap, int16_t* init_cls, int cls_of_zero) {
     const int64_t ntiles = urh_div_up(n, URH_TILE);
-    const unsigned grid = (unsigned)urh_div_up(ntiles, URH_WARPS_PER_BLOCK);
     const int vec_in = iq_vec_aligned(d_iq, DT) ? 1 : 0;
     const int vec_out = (d_qad && ((uintptr_t)d_qad % 8) == 0) ? 1 : 0;
+    const int threads = URH_WARPS_PER_BLOCK * 32;
+    auto generic = [&](int64_t begin, int64_t count) -> int {
+        if (count <= 0) return URH_OK;
+        URH_LAUNCH(ctx, (k_dense_iq<DT, MOD, DIG>), (unsigned)urh_div_up(count, URH_WARPS_PER_BLOCK), threads, 0, d_iq, n, dp,
+                   d_qad, vec_in, vec_out, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, begin, count);
+        return URH_OK;
+    };
+    // FSK on aligned buffers with a binary digitizer: tiles 1 .. nfull-1 take the packed-f32x2 kernel
+    const int64_t nfull = n / URH_TILE;
+    const bool fast = MOD == URH_MOD_FSK && vec_in && (!d_qad || vec_out) && (!DIG || cls.order == 2) && nfull > 1;
     URH_PROF_BEGIN(ctx);
-    URH_LAUNCH(ctx, (k_dense_iq<DT, MOD, DIG>), grid, URH_WARPS_PER_BLOCK * 32, 0, d_iq, n, dp, d_qad, vec_in,
-               vec_out, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero);
+    if (fast) {
+        const unsigned grid = (unsigned)urh_div_up(nfull - 1, URH_WARPS_PER_BLOCK);
+        if (d_qad)
+            URH_LAUNCH(ctx, (k_fsk_fast<DT, DIG, true>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
+                       tiles, staging, stage_cap, (int64_t)1, nfull - 1);
+        else
+            URH_LAUNCH(ctx, (k_fsk_fast<DT, DIG, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
+                       tiles, staging, stage_cap, (int64_t)1, nfull - 1);
+        URH_CHECK(generic(0, 1));
+        URH_CHECK(generic(nfull, ntiles - nfull));
+    } else {
+        URH_CHECK(generic(0, ntiles));
+    }
     URH_PROF_END(ctx);
     return URH_OK;
 }
