@@ -6,7 +6,7 @@
 #include "scan.cuh"
 #include "sparse.cuh"
 #ifndef URH_FAST_MIN_BLOCKS
-#define URH_FAST_MIN_BLOCKS 5
+#define URH_FAST_MIN_BLOCKS 4
 #endif
 #include "fsk_fast.cuh"
 #include "dense_f32.cuh"
