@@ -113,6 +113,33 @@ int urh_median_filter(urh_ctx* ctx, const double* d_x, int64_t n, unsigned int k
 /* replaces util.arr2decibel (util.pyx:38-48): count complex64 values -> float32 dB */
 int urh_arr2decibel(urh_ctx* ctx, const float* d_complex, int64_t count, float* d_out);
 
+/* ---- modulator (modulate.cu): replaces signal_functions.modulate_c / __modulate (signal_functions.pyx:56-177),
+ * get_gauss_filtered_freqs_phases (:196-226) for a BATCH of messages sharing one parameter set.
+ * d_bits: concatenated uint8 bits (OQPSK: already shuffled by get_oqpsk_bits and cut to the original length);
+ * h_bit_off[nmsg+1] bit offsets; h_out_off[nmsg+1] output sample offsets (symbols*sps + pause per message);
+ * d_out: (h_out_off[nmsg], 2) of out_dtype (URH_DT_I8 / I16 / F32), zero-filled by the call. */
+int urh_modulate_batch(urh_ctx* ctx, const uint8_t* d_bits, const int64_t* h_bit_off, const int64_t* h_out_off, int nmsg,
+                       uint32_t samples_per_symbol, int mod_type, const float* h_params, int nparams, int bits_per_symbol,
+                       float carrier_amplitude, float carrier_frequency, float carrier_phase, float sample_rate,
+                       uint32_t start, int out_dtype, const float* h_gauss_fir, int gauss_len, void* d_out);
+
+/* ---- filters (filter.cu) ----------------------------------------------------------------------------------
+ * urh_fir_filter replaces signal_functions.fir_filter (signal_functions.pyx:513-525), exact accumulation order;
+ * urh_convolve_c128: y[k] = full_convolution(x, taps)[k + offset], complex128 taps, double accumulation
+ *   (Filter.apply_bandpass_filter, Filter.py:84-101); urh_dc_correction: x - mean(x, axis=0) (Filter.py:32-33). */
+int urh_fir_filter(urh_ctx* ctx, const float* d_x, int64_t n, const float* d_taps, int m, float* d_y);
+int urh_convolve_c128(urh_ctx* ctx, const float* d_x, int64_t n, const double* d_taps, int m, int64_t offset,
+                      int64_t out_len, float* d_y);
+int urh_dc_correction(urh_ctx* ctx, const float* d_iq, int64_t n, float* d_out, int exact_order);
+
+/* ---- spectrogram (spectrogram.cu; cuFFT for the FFT only) -------------------------------------------------
+ * urh_stft replaces Spectrogram.stft (Spectrogram.py:94-116): complex128 [num_frames][window_size] = fft(frames*window)/W;
+ * urh_spectrogram_db replaces __calculate_spectrogram (:156-162): float32 fliplr(10*log10(|fftshift(stft)|^2)). */
+int urh_stft(urh_ctx* ctx, const float* d_x, int64_t n, int window_size, int hop, const double* d_window, int64_t num_frames,
+             double* d_out);
+int urh_spectrogram_db(urh_ctx* ctx, const float* d_x, int64_t n, int window_size, int hop, const double* d_window,
+                       int64_t num_frames, float* d_out);
+
 /* ---- measurement utilities (not part of the reference's API surface) -------------------------------- */
 /* CUDA-event timing of the dominant (dense, sample-rate) kernel of the last demod/digitize call */
 int urh_set_profiling(urh_ctx* ctx, int enabled);

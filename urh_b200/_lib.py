@@ -87,6 +87,12 @@ SIGNATURES = {
     "urh_plateau_lengths": (i32, [vp, vp, i64, f32, i32, vp, i64, C.POINTER(i64)]),
     "urh_median_filter": (i32, [vp, vp, i64, C.c_uint, vp]),
     "urh_arr2decibel": (i32, [vp, vp, i64, vp]),
+    "urh_modulate_batch": (i32, [vp, vp, vp, vp, i32, u32, i32, vp, i32, i32, f32, f32, f32, f32, u32, i32, vp, i32, vp]),
+    "urh_fir_filter": (i32, [vp, vp, i64, vp, i32, vp]),
+    "urh_convolve_c128": (i32, [vp, vp, i64, vp, i32, i64, i64, vp]),
+    "urh_dc_correction": (i32, [vp, vp, i64, vp, i32]),
+    "urh_stft": (i32, [vp, vp, i64, i32, i32, vp, i64, vp]),
+    "urh_spectrogram_db": (i32, [vp, vp, i64, i32, i32, vp, i64, vp]),
     "urh_set_profiling": (i32, [vp, i32]),
     "urh_last_dense_ms": (i32, [vp, C.POINTER(f32)]),
     "urh_selftest_packed_div": (i32, [vp, C.c_uint64, i64, C.POINTER(i64), C.POINTER(i64)]),

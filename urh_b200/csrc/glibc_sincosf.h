@@ -1,5 +1,6 @@
-// Bit-faithful restatement of glibc 2.39 sinf / cosf for |x| < 120 (the only range the Costas loop of
-// the reference, signal_functions.pyx:301, can produce: its phase is wrapped to +-2*pi every sample).
+// Bit-faithful restatement of glibc 2.39 sinf / cosf for every finite argument: the small / medium ranges the
+// Costas loop needs (signal_functions.pyx:301, phase wrapped to +-2*pi) and the large-argument reduction the
+// modulator needs (signal_functions.pyx:163-166: 2*pi*f*t reaches 1e5..1e7 rad).
 //
 // Provenance of every constant and of the operation order: NOT glibc source, but the machine code and
 // .rodata of THIS image's /usr/lib/x86_64-linux-gnu/libm.so.6 (glibc 2.39-0ubuntu8.5, build-id
@@ -67,7 +68,35 @@ URH_SC_HD float urh_sc_cos_poly(double x2, int neg) {
     return URH_D2F(URH_DFMA(c2p, x6, c));
 }
 
-// *ok = 0 when |y| >= 120 or non-finite (outside the restated range)
+// 4/pi in 32-bit words, __inv_pio4[24] of s_sincosf_data.c — read from libm.so.6 .rodata at 0xb80c0
+#if defined(__CUDA_ARCH__)
+#define URH_SC_TABLE static __device__ const
+#else
+#define URH_SC_TABLE static const
+#endif
+URH_SC_TABLE uint32_t urh_inv_pio4[24] = {
+    0x000000a2, 0x0000a2f9, 0x00a2f983, 0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529,
+    0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0,
+    0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041};
+#define URH_SC_PI63 0x1.921fb54442d18p-62
+
+// reduce_large (code at 0x7e92b of the FMA sinf): x mod pi/2 for 120 <= |x| < inf, quadrant in *np
+URH_SC_HD double urh_sc_reduce_large(uint32_t xi, int* np) {
+    const uint32_t* arr = &urh_inv_pio4[(xi >> 26) & 15];
+    const int shift = (xi >> 23) & 7;
+    const uint32_t m = ((xi & 0x7fffffu) | 0x800000u) << shift;
+    const uint32_t r0 = m * arr[0];
+    const uint64_t res1 = (uint64_t)m * arr[4];
+    const uint64_t res2 = (uint64_t)m * arr[8];
+    uint64_t res0 = (res2 >> 32) | ((uint64_t)r0 << 32);
+    res0 += res1;
+    const uint64_t n = (res0 + (1ull << 61)) >> 62;
+    res0 -= n << 62;
+    *np = (int)n;
+    return URH_DMUL((double)(int64_t)res0, URH_SC_PI63);
+}
+
+// *ok = 0 only for inf / nan
 URH_SC_HD void urh_glibc_sincosf(float y, float* sn, float* cs, int* ok) {
     const uint32_t top = (URH_SC_F2U(y) >> 20) & 0x7ff;
     const double x = (double)y;
@@ -83,10 +112,28 @@ URH_SC_HD void urh_glibc_sincosf(float y, float* sn, float* cs, int* ok) {
         *cs = urh_sc_cos_poly(x2, 0);
         return;
     }
-    if (top > 0x42e) {  // |y| >= 120: reduce_large / inf / nan — not restated
-        *ok = 0;
-        *sn = 0.0f;
-        *cs = 0.0f;
+    if (top > 0x42e) {  // |y| >= 120
+        if (top >= 0x7f8) {  // inf / nan
+            *ok = 0;
+            *sn = 0.0f;
+            *cs = 0.0f;
+            return;
+        }
+        const uint32_t xi = URH_SC_F2U(y);
+        int n;
+        const double xr = urh_sc_reduce_large(xi, &n);
+        const int ns = n + (int)(xi >> 31);
+        const int neg = (ns & 2) ? 1 : 0;
+        const double sign = ((ns & 3) == 1 || (ns & 3) == 2) ? -1.0 : 1.0;
+        const double x2 = URH_DMUL(xr, xr);
+        const double xs = URH_DMUL(xr, sign);
+        if (n & 1) {
+            *sn = urh_sc_cos_poly(x2, neg);
+            *cs = urh_sc_sin_poly(xs, x2);
+        } else {
+            *sn = urh_sc_sin_poly(xs, x2);
+            *cs = urh_sc_cos_poly(x2, neg);
+        }
         return;
     }
     const double r = URH_DMUL(x, URH_SC_HPI_INV);

@@ -121,3 +121,130 @@ def demod_digitize(samples, noise_mag: float, mod_type: str, center: float, tole
     if qad is not None and not on_device:
         qad = qad.get()
     return qad, rows
+
+
+# ---- modulator ------------------------------------------------------------------------------------------------
+def get_oqpsk_bits(original_bits) -> np.ndarray:
+    """signal_functions.pyx:179-193 (host; a bit shuffle on a few thousand bits)."""
+    bits = np.asarray(original_bits, dtype=np.uint8)
+    n = len(bits)
+    if n == 0:
+        return np.zeros(0, dtype=np.uint8)
+    out = np.zeros(n + 2, dtype=np.uint8)
+    out[0] = bits[0]
+    out[n + 1] = bits[n - 1]
+    idx = np.arange(2, n - 2, 2)
+    out[idx] = bits[idx]
+    out[idx + 1] = bits[idx - 1]
+    return out
+
+
+def gauss_fir(sample_rate: float, samples_per_symbol: int, bt: float = 0.5, filter_width: float = 1.0) -> np.ndarray:
+    """signal_functions.pyx:228-243 — Gaussian FIR taps (a few hundred values, host numpy exactly as the reference)."""
+    sample_rate = np.float32(sample_rate)
+    bt = np.float32(bt)
+    filter_width = np.float32(filter_width)
+    k = np.arange(-int(filter_width * samples_per_symbol), int(filter_width * samples_per_symbol) + 1, dtype=np.float32)
+    ts = np.float32(np.float32(samples_per_symbol) / sample_rate)
+    h = (np.sqrt((2 * np.pi) / (np.log(2))) * bt / ts
+         * np.exp(-(((np.sqrt(2) * np.pi) / np.sqrt(np.log(2)) * bt * k / samples_per_symbol) ** 2))).astype(np.float32)
+    return h / h.sum()
+
+
+_MOD_CODES = {"ask": _lib.MOD_ASK, "fsk": _lib.MOD_FSK, "psk": _lib.MOD_PSK, "gfsk": _lib.MOD_GFSK, "oqpsk": _lib.MOD_OQPSK}
+
+
+def modulate_batch(messages, samples_per_symbol, modulation_type, parameters, bits_per_symbol, carrier_amplitude,
+                   carrier_frequency, carrier_phase, sample_rate, pauses, start=0, dtype=np.float32, gauss_bt=0.5,
+                   filter_width=1.0, device_result=False):
+    """Modulate a batch of bit arrays that share one parameter set in ONE launch sequence (B200 addition; per message
+    the result equals modulate_c(bits, ..., pause, start)).  Returns a list of (total,2) arrays (or one DeviceArray +
+    offsets when device_result=True)."""
+    dtype = np.dtype(dtype)
+    if dtype not in (np.dtype(np.int8), np.dtype(np.int16), np.dtype(np.float32)):
+        raise ValueError("Unsupported dtype for modulation {}".format(dtype))
+    mod = modulation_type.lower()
+    assert mod in _MOD_CODES
+    if mod == "oqpsk":
+        assert bits_per_symbol == 2
+    ctx = _lib.default_context()
+    msgs = []
+    for bits in messages:
+        b = np.ascontiguousarray(np.asarray(bits, dtype=np.uint8))
+        if mod == "oqpsk" and len(b):
+            b = np.ascontiguousarray(get_oqpsk_bits(b)[: len(b)])  # only the first len(bits) shuffled bits are used
+        msgs.append(b)
+    nmsg = len(msgs)
+    pauses = [int(p) for p in (pauses if hasattr(pauses, "__len__") else [pauses] * nmsg)]
+    bit_off = np.zeros(nmsg + 1, dtype=np.int64)
+    out_off = np.zeros(nmsg + 1, dtype=np.int64)
+    for m, b in enumerate(msgs):
+        bit_off[m + 1] = bit_off[m] + len(b)
+        nsym = int(len(b) // bits_per_symbol)
+        out_off[m + 1] = out_off[m] + nsym * int(samples_per_symbol) + pauses[m]
+    total = int(out_off[-1])
+    params = np.ascontiguousarray(np.asarray(parameters, dtype=np.float32))
+    d_out = DeviceArray(ctx, (total, 2), dtype)
+    if total and bit_off[-1] > 0:
+        d_bits = to_device(np.concatenate(msgs) if nmsg else np.zeros(0, np.uint8), ctx)
+        gfir = gauss_fir(sample_rate, samples_per_symbol, bt=gauss_bt, filter_width=filter_width) if mod == "gfsk" else None
+        ctx.check(ctx.lib.urh_modulate_batch(
+            ctx.handle, C.c_void_p(d_bits.ptr), bit_off.ctypes.data_as(C.c_void_p), out_off.ctypes.data_as(C.c_void_p), nmsg,
+            int(samples_per_symbol), _MOD_CODES[mod], params.ctypes.data_as(C.c_void_p), len(params), int(bits_per_symbol),
+            float(carrier_amplitude), float(carrier_frequency), float(carrier_phase), float(sample_rate), int(start),
+            _lib.dtype_code(dtype), gfir.ctypes.data_as(C.c_void_p) if gfir is not None else None,
+            len(gfir) if gfir is not None else 0, C.c_void_p(d_out.ptr)))
+    elif total:
+        d_out.zero()
+    if device_result:
+        return d_out, out_off
+    host = d_out.get()
+    return [host[out_off[m]: out_off[m + 1]] for m in range(nmsg)]
+
+
+def modulate_c(bits, samples_per_symbol, modulation_type, parameters, bits_per_symbol, carrier_amplitude,
+               carrier_frequency, carrier_phase, sample_rate, pause, start, dtype=np.float32, gauss_bt=0.5, filter_width=1.0):
+    """signal_functions.pyx:56-177 — one message."""
+    dtype_np = np.dtype(dtype) if dtype in (np.int8, np.int16, np.float32) or isinstance(dtype, np.dtype) else None
+    if dtype_np is None or dtype_np not in (np.dtype(np.int8), np.dtype(np.int16), np.dtype(np.float32)):
+        raise ValueError("Unsupported dtype for modulation {}".format(dtype))
+    bits = np.asarray(bits, dtype=np.uint8)
+    if len(bits) == 0:
+        return np.zeros((int(pause), 2), dtype=dtype_np)
+    assert modulation_type.lower() in _MOD_CODES
+    return modulate_batch([bits], samples_per_symbol, modulation_type, parameters, bits_per_symbol, carrier_amplitude,
+                          carrier_frequency, carrier_phase, sample_rate, [pause], start, dtype_np, gauss_bt, filter_width)[0]
+
+
+# ---- filters ----------------------------------------------------------------------------------------------------
+def fir_filter(input_samples, filter_taps):
+    """signal_functions.pyx:513-525 — causal complex64 FIR, exact accumulation order."""
+    on_device = isinstance(input_samples, DeviceArray)
+    ctx = input_samples.ctx if on_device else _lib.default_context()
+    if not on_device:
+        if not isinstance(input_samples, np.ndarray) or input_samples.dtype != np.complex64 or input_samples.ndim != 1:
+            raise ValueError("Buffer dtype mismatch, expected 'float complex'")
+        input_samples = np.ascontiguousarray(input_samples)
+    taps = np.ascontiguousarray(np.asarray(filter_taps, dtype=np.complex64))
+    n = len(input_samples)
+    out = DeviceArray(ctx, (n,), np.complex64)
+    if n:
+        d = input_samples if on_device else to_device(input_samples.view(np.float32), ctx)
+        d_t = to_device(taps.view(np.float32) if len(taps) else np.zeros(2, np.float32), ctx)
+        ctx.check(ctx.lib.urh_fir_filter(ctx.handle, C.c_void_p(d.ptr), n, C.c_void_p(d_t.ptr), len(taps), C.c_void_p(out.ptr)))
+    return out if on_device else out.get()
+
+
+def iir_filter(a, b, signal):
+    """signal_functions.pyx:527-542 — only caller is an exploratory test script; serial recurrence on tiny inputs."""
+    raise NotImplementedError("iir_filter has no caller on the IQ hot path (SURVEY §8b)")
+
+
+def find_nearest_center(sample: float, centers, num_centers: int) -> int:
+    """signal_functions.pyx:497-511 (no caller in the reference)."""
+    best, best_d = 0, np.float32(99999)
+    for i in range(num_centers):
+        d = np.float32((np.float32(sample) - np.float32(centers[i])) ** 2)
+        if d < best_d:
+            best_d, best = d, i
+    return best

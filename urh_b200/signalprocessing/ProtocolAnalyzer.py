@@ -1,0 +1,128 @@
+"""Pulses -> bits: the caller side of the digitizer (reference: ProtocolAnalyzer.get_protocol_from_signal
+ProtocolAnalyzer.py:227-285 and _ppseq_to_bits :323-414).  Only what is needed to turn the pulse table into the bit
+strings the reference's demodulation tests assert on; the protocol container / labels / decodings are out of scope.
+The Python loop over the k pulse rows is row f-1 of the scope table ("next": move to the device)."""
+import array
+
+import numpy as np
+
+from ..cythonext import signal_functions
+
+
+def number_to_bits(n: int, length: int) -> list:
+    """util.number_to_bits (src/urh/util/util.py): MSB-first bit list of fixed length"""
+    return [int(c) for c in format(int(n), "0{}b".format(length))]
+
+
+class LiteMessage(object):
+    def __init__(self, bits, pause, bit_sample_pos, rssi=0.0):
+        self.plain_bits = bits
+        self.pause = pause
+        self.bit_sample_pos = bit_sample_pos
+        self.rssi = rssi
+
+    @property
+    def plain_bits_str(self) -> str:
+        return "".join(map(str, self.plain_bits))
+
+    def __len__(self):
+        return len(self.plain_bits)
+
+
+class ProtocolAnalyzer(object):
+    def __init__(self, signal):
+        self.signal = signal
+        self.messages = []
+
+    @property
+    def plain_bits_str(self):
+        return [m.plain_bits_str for m in self.messages]
+
+    @property
+    def plain_hex_str(self):
+        out = []
+        for m in self.messages:
+            s = m.plain_bits_str
+            s += "0" * ((4 - len(s) % 4) % 4)
+            out.append("".join("{:x}".format(int(s[i:i + 4], 2)) for i in range(0, len(s), 4)))
+        return out
+
+    def get_protocol_from_signal(self):
+        signal = self.signal
+        self.messages = []
+        if signal is None:
+            return
+        qad = signal.qad_device if hasattr(signal, "qad_device") else signal.qad
+        ppseq = signal_functions.grab_pulse_lens(
+            qad, signal.center, signal.tolerance, signal.modulation_type, signal.samples_per_symbol,
+            signal.bits_per_symbol, signal.center_spacing)
+        bit_data, pauses, bit_sample_pos = self._ppseq_to_bits(
+            ppseq, signal.samples_per_symbol, signal.bits_per_symbol, pause_threshold=signal.pause_threshold)
+        if signal.message_length_divisor > 1 and signal.modulation_type == "ASK":
+            self._ensure_message_length_multiple(bit_data, signal.samples_per_symbol, pauses, bit_sample_pos, signal.message_length_divisor)
+        for i, (bits, pause) in enumerate(zip(bit_data, pauses)):
+            middle = bit_sample_pos[i][int(len(bits) / 2)]
+            rssi = np.mean(signal.iq_array.subarray(middle, middle + signal.samples_per_symbol).magnitudes_normalized)
+            self.messages.append(LiteMessage(bits, pause, bit_sample_pos[i], rssi))
+
+    @staticmethod
+    def _ensure_message_length_multiple(bit_data, samples_per_symbol, pauses, bit_sample_pos, divisor):
+        for i in range(len(bit_data)):
+            missing = (divisor - (len(bit_data[i]) % divisor)) % divisor
+            if missing > 0 and pauses[i] >= samples_per_symbol * missing:
+                bit_data[i].extend([0] * missing)
+                pauses[i] = pauses[i] - missing * samples_per_symbol
+                try:
+                    bit_sample_pos[i][-1] = bit_sample_pos[i][-2] + samples_per_symbol
+                except IndexError:
+                    continue
+                bit_sample_pos[i].extend([bit_sample_pos[i][-1] + (k + 1) * samples_per_symbol for k in range(missing - 1)])
+                bit_sample_pos[i].append(bit_sample_pos[i][-1] + pauses[i])
+
+    @staticmethod
+    def _ppseq_to_bits(ppseq, samples_per_symbol, bits_per_symbol, write_bit_sample_pos=True, pause_threshold=8):
+        positions, all_positions = array.array("L", []), []
+        bits, all_bits = array.array("B", []), []
+        pauses = array.array("L", [])
+        first, total = 0, 0
+        there_was_data = False
+        samples_per_bit = int(samples_per_symbol / bits_per_symbol)
+        if len(ppseq) > 0 and ppseq[0, 0] == -1:
+            first, total = 1, int(ppseq[0, 1])  # capture starts with a pause
+        for i in range(first, len(ppseq)):
+            kind, num_samples = int(ppseq[i, 0]), int(ppseq[i, 1])
+            num_symbols_float = num_samples / samples_per_symbol
+            num_symbols = int(num_symbols_float)
+            if num_symbols_float - num_symbols > 0.5:
+                num_symbols += 1
+            if kind == -1:
+                if num_symbols <= pause_threshold or pause_threshold == 0:
+                    bits.extend([0] * (num_symbols * bits_per_symbol))
+                    if write_bit_sample_pos:
+                        positions.extend([total + k * samples_per_bit for k in range(num_symbols * bits_per_symbol)])
+                elif not there_was_data:
+                    bits = array.array("B", [])
+                    positions = array.array("L", [])
+                else:
+                    if write_bit_sample_pos:
+                        positions.append(total)
+                        positions.append(total + num_samples)
+                        all_positions.append(positions[:])
+                        positions = array.array("L", [])
+                    all_bits.append(bits[:])
+                    bits = array.array("B", [])
+                    pauses.append(num_samples)
+                    there_was_data = False
+            else:
+                bits.extend(number_to_bits(kind, bits_per_symbol) * num_symbols)
+                if not there_was_data and num_symbols > 0:
+                    there_was_data = True
+                if write_bit_sample_pos:
+                    positions.extend([total + k * samples_per_bit for k in range(num_symbols * bits_per_symbol)])
+            total += num_samples
+        if there_was_data:
+            all_bits.append(bits[:])
+            if write_bit_sample_pos:
+                all_positions.append(positions[:] + array.array("L", [total]))
+            pauses.append(int(ppseq[-1, 1]) if ppseq[-1, 0] == -1 else 0)
+        return all_bits, pauses, all_positions
