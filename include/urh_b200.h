@@ -140,6 +140,27 @@ int urh_stft(urh_ctx* ctx, const float* d_x, int64_t n, int window_size, int hop
 int urh_spectrogram_db(urh_ctx* ctx, const float* d_x, int64_t n, int window_size, int hop, const double* d_window,
                        int64_t num_frames, float* d_out);
 
+/* ---- sharded captures: one contiguous sample range per GPU (digitize.cu, nccl.cu) ----------
+ * urh_shard_dense      every rank: demodulate + classify its shard (d_iq[-1] = halo sample when has_halo);
+ *                      h_summary = {last_cls, last_len, whole, init_cls}
+ * urh_shard_candidates every rank, after exchanging the summaries: candidate table with GLOBAL positions
+ * urh_pulses_from_table the gathering rank: concatenated tables -> (state, length) rows of the whole capture */
+int urh_shard_dense(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int has_halo, float noise_mag, int mod_type,
+                    float center, uint16_t tolerance, uint8_t bits_per_symbol, float center_spacing, float* d_qad_out,
+                    int64_t* h_summary);
+int urh_shard_candidates(urh_ctx* ctx, int carry_valid, int carry_cls, int64_t carry_len, int64_t global_offset,
+                         int64_t* count, const int64_t** d_pos, const int16_t** d_cls);
+int urh_pulses_from_table(urh_ctx* ctx, const int64_t* d_pos, const int16_t* d_cls, int64_t count, int64_t n_total,
+                          uint16_t tolerance, int mod_type, uint32_t samples_per_symbol, int init_cls, int64_t* k);
+/* NCCL (dlopen'ed libnccl.so.2): id from rank 0 is distributed by the launcher plumbing */
+int urh_nccl_unique_id(char* out128);
+int urh_nccl_init(urh_ctx* ctx, const char* id128, int rank, int world);
+int urh_nccl_destroy(urh_ctx* ctx);
+int urh_nccl_allreduce_f64(urh_ctx* ctx, double* d_buf, int64_t count, int op);   /* op: 0 sum, 1 max, 2 min */
+int urh_nccl_allreduce_i64(urh_ctx* ctx, int64_t* d_buf, int64_t count, int op);
+int urh_nccl_allgather(urh_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
+int urh_nccl_gatherv(urh_ctx* ctx, const void* d_send, void* d_recv, const int64_t* h_bytes, int root);
+
 /* ---- measurement utilities (not part of the reference's API surface) -------------------------------- */
 /* CUDA-event timing of the dominant (dense, sample-rate) kernel of the last demod/digitize call */
 int urh_set_profiling(urh_ctx* ctx, int enabled);

@@ -1,0 +1,62 @@
+"""Worker for tests/test_gpu_dist.py: launched under torchrun with one rank per GPU.  Compares the sharded
+demod+digitize / noise detection (urh_b200.dist, NCCL) with the single-GPU result on the same capture."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch.distributed as dist
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from conftest import synth_fsk
+    from urh_b200 import _lib, dist as udist
+    from urh_b200.device import DeviceArray, to_device
+    from urh_b200.cythonext import signal_functions as sf
+    from urh_b200.ainterpretation import AutoInterpretation as AI
+
+    ctx = _lib.default_context(int(os.environ.get("LOCAL_RANK", rank)))
+    hx = udist.HostExchange()
+    udist.init_nccl(ctx, hx)
+    failures = []
+    for case, (n, sps, tol, mod, dtype) in enumerate([
+        (3_000_000, 100, 5, "FSK", np.float32), (1_000_003, 37, 0, "FSK", np.float32), (700_001, 50, 9, "ASK", np.float32),
+        (2_500_000, 100, 5000, "FSK", np.float32), (900_000, 64, 3, "FSK", np.int16),
+    ]):
+        iq = synth_fsk(n, sps=sps, seed=17 + case, gap_every=n // 7, dtype=dtype)
+        if mod == "ASK":
+            env = np.repeat(np.random.default_rng(case).integers(0, 2, n // sps + 1), sps)[:n] * 0.9 + 0.1
+            iq = (iq.astype(np.float32) * env[:, None]).astype(dtype)
+        noise = 0.05 if dtype == np.float32 else 1000.0
+        center = 0.0 if mod == "FSK" else 0.3
+        lo, hi = udist.shard_bounds(n, world)[rank]
+        sb = udist.ShardBuffer(ctx, hi - lo, dtype)
+        sb.shard.set(iq[lo:hi])
+        udist.exchange_halo(ctx, hx, sb)
+        d_qad = DeviceArray(ctx, (hi - lo,), np.float32)
+        rows = udist.demod_digitize_sharded(ctx, hx, sb, lo, n, noise, mod, center, tol, sps, d_qad=d_qad)
+        qads = hx.allgather(d_qad.get())
+        noise_sh = udist.detect_noise_level_sharded(ctx, hx, sb, lo, n)
+        if rank == 0:
+            qad_ref, rows_ref = sf.demod_digitize(iq, noise, mod, center, tol, sps)
+            if not np.array_equal(np.concatenate(qads).view(np.uint32), qad_ref.view(np.uint32)):
+                failures.append(("qad", case))
+            if not np.array_equal(rows, rows_ref):
+                failures.append(("rows", case, len(rows), len(rows_ref)))
+            if noise_sh != AI.detect_noise_level_iq(iq):
+                failures.append(("noise", case, noise_sh))
+    res = hx.allgather(failures)
+    if rank == 0:
+        flat = [f for part in res for f in part]
+        print("DIST_GPU_RESULT", "OK" if not flat else flat)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

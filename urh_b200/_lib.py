@@ -93,6 +93,16 @@ SIGNATURES = {
     "urh_dc_correction": (i32, [vp, vp, i64, vp, i32]),
     "urh_stft": (i32, [vp, vp, i64, i32, i32, vp, i64, vp]),
     "urh_spectrogram_db": (i32, [vp, vp, i64, i32, i32, vp, i64, vp]),
+    "urh_shard_dense": (i32, [vp, vp, i32, i64, i32, f32, i32, f32, u16, u8, f32, vp, vp]),
+    "urh_shard_candidates": (i32, [vp, i32, i32, i64, i64, C.POINTER(i64), C.POINTER(vp), C.POINTER(vp)]),
+    "urh_pulses_from_table": (i32, [vp, vp, vp, i64, i64, u16, i32, u32, i32, C.POINTER(i64)]),
+    "urh_nccl_unique_id": (i32, [vp]),
+    "urh_nccl_init": (i32, [vp, vp, i32, i32]),
+    "urh_nccl_destroy": (i32, [vp]),
+    "urh_nccl_allreduce_f64": (i32, [vp, vp, i64, i32]),
+    "urh_nccl_allreduce_i64": (i32, [vp, vp, i64, i32]),
+    "urh_nccl_allgather": (i32, [vp, vp, vp, szt]),
+    "urh_nccl_gatherv": (i32, [vp, vp, vp, vp, i32]),
     "urh_set_profiling": (i32, [vp, i32]),
     "urh_last_dense_ms": (i32, [vp, C.POINTER(f32)]),
     "urh_selftest_packed_div": (i32, [vp, C.c_uint64, i64, C.POINTER(i64), C.POINTER(i64)]),

@@ -46,6 +46,11 @@ struct urh_ctx {
     int fft_nfft;
     int64_t fft_batch;
     bool fft_valid;
+    // sharded digitizer state between urh_shard_dense and urh_shard_candidates (arena memory)
+    void* shard_tiles;
+    void* shard_staging;
+    int shard_cap, shard_tol;
+    int64_t shard_n;
     // NCCL (nccl.cu)
     void* nccl_comm;
     int nccl_rank, nccl_world;

@@ -27,6 +27,8 @@ extern "C" int urh_ctx_create(int device, urh_ctx** out) {
     ctx->h_stage[0] = ctx->h_stage[1] = nullptr;
     ctx->h_stage_bytes = 0;
     ctx->fft_valid = false;
+    ctx->shard_tiles = nullptr;
+    ctx->shard_staging = nullptr;
     ctx->nccl_comm = nullptr;
     ctx->nccl_rank = 0;
     ctx->nccl_world = 1;

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32)
 k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __restrict__ qad_out, int vec_in,
            int vec_out, const __grid_constant__ UrhClassify cls, int tol, UrhTileSummary* __restrict__ tiles,
            uint32_t* __restrict__ staging, int stage_cap, int16_t* __restrict__ init_cls, int cls_of_zero,
-           int64_t tile_begin, int64_t tile_count) {
+           int64_t tile_begin, int64_t tile_count, int has_halo) {
     const int lane = threadIdx.x & 31;
     const int64_t tile_rel = (int64_t)blockIdx.x * URH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (tile_rel >= tile_count) return;
@@ -38,9 +38,11 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
 
     // FSK: (A, B) terms of the sample preceding the tile's first sample
     float cA = 0.0f, cB = 0.0f;
-    if (MOD == URH_MOD_FSK && tile_start > 0 && lane == 0) {
-        const UrhPair pv = urh_load_pair<DT>(iq, tile_start - 1, n, false);
-        const UrhFskTerms t = urh_fsk_terms(pv.r0, pv.i0);
+    // (a shard of a larger capture has its predecessor sample stored right before iq: has_halo)
+    if (MOD == URH_MOD_FSK && (tile_start > 0 || has_halo) && lane == 0) {
+        typedef typename UrhElem<DT>::type E;
+        const E* pp = (const E*)iq + 2 * (tile_start - 1);
+        const UrhFskTerms t = urh_fsk_terms((float)pp[0], (float)pp[1]);
         cA = t.A; cB = t.B;
     }
 
@@ -68,7 +70,7 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
             if (!(m0 <= dp.noise_sqrd)) s0 = __fdiv_rn(__fsqrt_rn(m0), dp.max_mag);
             if (!(m1 <= dp.noise_sqrd)) s1 = __fdiv_rn(__fsqrt_rn(m1), dp.max_mag);
         }
-        if (pos0 == 0) s0 = dp.noise_value;  // result[0] = NOISE (pyx:361)
+        if (pos0 == 0 && !has_halo) s0 = dp.noise_value;  // result[0] = NOISE (pyx:361); shards: only the capture's first sample
 
         const bool v0 = pos0 < n, v1 = pos0 + 1 < n;
         if (qad_out) {
@@ -159,7 +161,7 @@ static bool iq_vec_aligned(const void* p, int dtype) { return ((uintptr_t)p % (2
 template <int DT, int MOD, bool DIG>
 static int launch_dense_iq_t(urh_ctx* ctx, const void* d_iq, int64_t n, const UrhDemodParams& dp, float* d_qad,
                              const UrhClassify& cls, int tol, UrhTileSummary* tiles, uint32_t* staging,
-                             int stage_cap, int16_t* init_cls, int cls_of_zero) {
+                             int stage_cap, int16_t* init_cls, int cls_of_zero, int has_halo = 0) {
     const int64_t ntiles = urh_div_up(n, URH_TILE);
     const int vec_in = iq_vec_aligned(d_iq, DT) ? 1 : 0;
     const int vec_out = (d_qad && ((uintptr_t)d_qad % 8) == 0) ? 1 : 0;
@@ -167,7 +169,7 @@ static int launch_dense_iq_t(urh_ctx* ctx, const void* d_iq, int64_t n, const Ur
     auto generic = [&](int64_t begin, int64_t count) -> int {
         if (count <= 0) return URH_OK;
         URH_LAUNCH(ctx, (k_dense_iq<DT, MOD, DIG>), (unsigned)urh_div_up(count, URH_WARPS_PER_BLOCK), threads, 0, d_iq, n, dp,
-                   d_qad, vec_in, vec_out, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, begin, count);
+                   d_qad, vec_in, vec_out, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, begin, count, has_halo);
         return URH_OK;
     };
     // FSK on aligned buffers with a binary digitizer: tiles 1 .. nfull-1 take the packed-f32x2 kernel
@@ -194,13 +196,13 @@ static int launch_dense_iq_t(urh_ctx* ctx, const void* d_iq, int64_t n, const Ur
 template <int MOD, bool DIG>
 static int launch_dense_iq_m(urh_ctx* ctx, int dtype, const void* d_iq, int64_t n, const UrhDemodParams& dp,
                              float* d_qad, const UrhClassify& cls, int tol, UrhTileSummary* tiles,
-                             uint32_t* staging, int stage_cap, int16_t* init_cls, int cls_of_zero) {
+                             uint32_t* staging, int stage_cap, int16_t* init_cls, int cls_of_zero, int has_halo = 0) {
     switch (dtype) {
-        case URH_DT_I8: return launch_dense_iq_t<URH_DT_I8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero);
-        case URH_DT_U8: return launch_dense_iq_t<URH_DT_U8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero);
-        case URH_DT_I16: return launch_dense_iq_t<URH_DT_I16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero);
-        case URH_DT_U16: return launch_dense_iq_t<URH_DT_U16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero);
-        case URH_DT_F32: return launch_dense_iq_t<URH_DT_F32, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero);
+        case URH_DT_I8: return launch_dense_iq_t<URH_DT_I8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo);
+        case URH_DT_U8: return launch_dense_iq_t<URH_DT_U8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo);
+        case URH_DT_I16: return launch_dense_iq_t<URH_DT_I16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo);
+        case URH_DT_U16: return launch_dense_iq_t<URH_DT_U16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo);
+        case URH_DT_F32: return launch_dense_iq_t<URH_DT_F32, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo);
         default: URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
     }
 }
@@ -325,6 +327,86 @@ extern "C" int urh_demod_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int
     else
         URH_CHECK((launch_dense_iq_m<URH_MOD_FSK, true>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, tol, tiles, staging, cap, d_init, c0)));
     return digitize_finish(ctx, n, tol, mod_type == URH_MOD_ASK, samples_per_symbol, tiles, staging, cap, d_init, k);
+}
+
+// =====================================================================================================
+// Sharded captures: one contiguous sample range per GPU, 1-sample halo for the FSK conjugate
+// product, run-carry descriptors exchanged between ranks, candidate tables gathered to one rank.
+// =====================================================================================================
+// Step 1 on every rank.  d_iq points at the shard's first own sample; when has_halo != 0 the sample that precedes
+// the shard in the capture is stored immediately before it (d_iq[-1]).  Keeps the tile table in the arena for step 2.
+// h_summary = {last_cls, last_len, whole, init_cls}: the shard's closing run and (rank 0) the digitizer's initial state.
+extern "C" int urh_shard_dense(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int has_halo, float noise_mag, int mod_type,
+                               float center, uint16_t tolerance, uint8_t bits_per_symbol, float center_spacing,
+                               float* d_qad_out, int64_t* h_summary) {
+    if (n <= 0) URH_FAIL(ctx, URH_ERR_INVALID, "empty shard");
+    if (mod_type != URH_MOD_ASK && mod_type != URH_MOD_FSK) URH_FAIL(ctx, URH_ERR_INVALID, "sharded path: ASK / FSK only (PSK is a serial recurrence)");
+    if (urh_iq_bytes(dtype) == 0) URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
+    urh_arena_reset(ctx);
+    UrhClassify cls;
+    URH_CHECK(fill_classify(ctx, &cls, mod_type, center, bits_per_symbol, center_spacing));
+    const UrhDemodParams dp = make_demod_params(noise_mag, mod_type, dtype);
+    const int tol = tolerance;
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    const int cap = stage_cap_for(tol);
+    UrhTileSummary* tiles;
+    uint32_t* staging;
+    int16_t* d_init;
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles, &tiles));
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles * cap, &staging));
+    URH_CHECK(urh_arena(ctx, 8, &d_init));
+    URH_CUDA(ctx, cudaMemsetAsync(d_init, 0, 16, ctx->stream));
+    const int c0 = host_classify(0.0f, cls);
+    if (mod_type == URH_MOD_ASK)
+        URH_CHECK((launch_dense_iq_m<URH_MOD_ASK, true>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, tol, tiles, staging, cap, d_init, c0, has_halo)));
+    else
+        URH_CHECK((launch_dense_iq_m<URH_MOD_FSK, true>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, tol, tiles, staging, cap, d_init, c0, has_halo)));
+    ctx->shard_tiles = tiles;
+    ctx->shard_staging = staging;
+    ctx->shard_cap = cap;
+    ctx->shard_n = n;
+    ctx->shard_tol = tol;
+    URH_CHECK(urh_shard_run_total(ctx, n, tiles, h_summary));
+    int16_t init16 = 0;
+    URH_CUDA(ctx, cudaMemcpyAsync(&init16, d_init, sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    h_summary[3] = init16;
+    return URH_OK;
+}
+
+// Step 2 on every rank, after the summaries were exchanged: carry_* describe the run that ends right before this
+// shard (fold of the preceding shards' summaries; carry_valid = 0 on the first shard).  Positions are global.
+extern "C" int urh_shard_candidates(urh_ctx* ctx, int carry_valid, int carry_cls, int64_t carry_len, int64_t global_offset,
+                                    int64_t* count, const int64_t** d_pos, const int16_t** d_cls) {
+    if (!ctx->shard_tiles) URH_FAIL(ctx, URH_ERR_INVALID, "urh_shard_dense must precede urh_shard_candidates");
+    UrhShardCarry in;
+    in.valid = carry_valid; in.cls = carry_cls; in.len = carry_len;
+    UrhCandidates cand;
+    URH_CHECK(urh_collect_candidates_shard(ctx, ctx->shard_n, ctx->shard_tol, (const UrhTileSummary*)ctx->shard_tiles,
+                                           (const uint32_t*)ctx->shard_staging, ctx->shard_cap, in, global_offset, &cand));
+    *count = cand.count;
+    if (d_pos) *d_pos = cand.pos;
+    if (d_cls) *d_cls = cand.cls;
+    ctx->shard_tiles = nullptr;
+    return URH_OK;
+}
+
+// Step 3 on the gathering rank: the concatenated candidate tables of all shards -> pulse table of the whole capture.
+extern "C" int urh_pulses_from_table(urh_ctx* ctx, const int64_t* d_pos, const int16_t* d_cls, int64_t count, int64_t n_total,
+                                     uint16_t tolerance, int mod_type, uint32_t samples_per_symbol, int init_cls, int64_t* k) {
+    urh_arena_reset(ctx);
+    int16_t* d_init;
+    URH_CHECK(urh_arena(ctx, 8, &d_init));
+    const int16_t v = (int16_t)init_cls;
+    URH_CUDA(ctx, cudaMemcpyAsync(d_init, &v, sizeof(v), cudaMemcpyHostToDevice, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    UrhCandidates cand;
+    cand.count = count;
+    cand.pos = (int64_t*)d_pos;
+    cand.cls = (int16_t*)d_cls;
+    cand.last_cls = 0;
+    cand.last_len = 0;
+    return urh_pulses_from_candidates(ctx, n_total, tolerance, mod_type == URH_MOD_ASK, samples_per_symbol, cand, d_init, k);
 }
 
 extern "C" int urh_fetch_pulses(urh_ctx* ctx, int64_t* h_rows, int64_t k) {

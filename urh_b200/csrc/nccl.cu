@@ -1,0 +1,154 @@
+// NCCL plumbing for captures sharded across the GPUs of one box.
+// The exchanges on this path are tiny (chunk statistics, run-carry descriptors, histograms) plus one gather of the
+// sparse candidate tables; NVLink bandwidth is irrelevant, latency is what counts.  libnccl is dlopen()ed so that
+// liburh_b200.so has no link-time dependency on it (single-GPU users never load it) and cannot clash with another
+// NCCL copy in the process.
+#include "common.cuh"
+
+#include <dlfcn.h>
+
+typedef struct { char internal[128]; } urh_ncclUniqueId;
+typedef void* urh_ncclComm_t;
+typedef int urh_ncclResult_t;
+enum { URH_NCCL_SUM = 0, URH_NCCL_MAX = 2, URH_NCCL_MIN = 3 };
+enum { URH_NCCL_UINT8 = 1, URH_NCCL_INT64 = 4, URH_NCCL_FLOAT64 = 8 };
+
+static struct {
+    void* handle;
+    urh_ncclResult_t (*GetUniqueId)(urh_ncclUniqueId*);
+    urh_ncclResult_t (*CommInitRank)(urh_ncclComm_t*, int, urh_ncclUniqueId, int);
+    urh_ncclResult_t (*CommDestroy)(urh_ncclComm_t);
+    urh_ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, urh_ncclComm_t, cudaStream_t);
+    urh_ncclResult_t (*AllGather)(const void*, void*, size_t, int, urh_ncclComm_t, cudaStream_t);
+    urh_ncclResult_t (*Send)(const void*, size_t, int, int, urh_ncclComm_t, cudaStream_t);
+    urh_ncclResult_t (*Recv)(void*, size_t, int, int, urh_ncclComm_t, cudaStream_t);
+    urh_ncclResult_t (*GroupStart)(void);
+    urh_ncclResult_t (*GroupEnd)(void);
+    const char* (*GetErrorString)(urh_ncclResult_t);
+} g_nccl;
+
+static int nccl_load(char* err, size_t errlen) {
+    if (g_nccl.handle) return URH_OK;
+    const char* names[] = {getenv("URH_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        if (!n || !*n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+        if (h) break;
+    }
+    if (!h) {
+        snprintf(err, errlen, "cannot dlopen libnccl.so.2 (%s)", dlerror());
+        return URH_ERR_CUDA;
+    }
+#define LOADSYM(field, name)                                              \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                            \
+    if (!g_nccl.field) {                                                  \
+        snprintf(err, errlen, "libnccl: missing symbol %s", name);        \
+        dlclose(h);                                                       \
+        return URH_ERR_CUDA;                                              \
+    }
+    LOADSYM(GetUniqueId, "ncclGetUniqueId")
+    LOADSYM(CommInitRank, "ncclCommInitRank")
+    LOADSYM(CommDestroy, "ncclCommDestroy")
+    LOADSYM(AllReduce, "ncclAllReduce")
+    LOADSYM(AllGather, "ncclAllGather")
+    LOADSYM(Send, "ncclSend")
+    LOADSYM(Recv, "ncclRecv")
+    LOADSYM(GroupStart, "ncclGroupStart")
+    LOADSYM(GroupEnd, "ncclGroupEnd")
+    LOADSYM(GetErrorString, "ncclGetErrorString")
+#undef LOADSYM
+    g_nccl.handle = h;
+    return URH_OK;
+}
+
+#define URH_NCCL(ctx, call)                                                                              \
+    do {                                                                                                 \
+        urh_ncclResult_t r__ = (call);                                                                   \
+        if (r__ != 0) {                                                                                  \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,       \
+                     g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error");                 \
+            return URH_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+// rank 0 creates the id; the launcher plumbing (torch.distributed / env) broadcasts the 128 bytes
+extern "C" int urh_nccl_unique_id(char* out128) {
+    char err[256];
+    if (nccl_load(err, sizeof(err)) != URH_OK) return URH_ERR_CUDA;
+    urh_ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return URH_ERR_CUDA;
+    memcpy(out128, id.internal, 128);
+    return URH_OK;
+}
+
+extern "C" int urh_nccl_init(urh_ctx* ctx, const char* id128, int rank, int world) {
+    URH_CHECK(nccl_load(ctx->err, sizeof(ctx->err)));
+    URH_CUDA(ctx, cudaSetDevice(ctx->device));
+    urh_ncclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    urh_ncclComm_t comm = nullptr;
+    URH_NCCL(ctx, g_nccl.CommInitRank(&comm, world, id, rank));
+    ctx->nccl_comm = comm;
+    ctx->nccl_rank = rank;
+    ctx->nccl_world = world;
+    return URH_OK;
+}
+
+extern "C" int urh_nccl_destroy(urh_ctx* ctx) {
+    if (ctx->nccl_comm && g_nccl.CommDestroy) {
+        cudaStreamSynchronize(ctx->stream);
+        g_nccl.CommDestroy((urh_ncclComm_t)ctx->nccl_comm);
+    }
+    ctx->nccl_comm = nullptr;
+    ctx->nccl_world = 1;
+    ctx->nccl_rank = 0;
+    return URH_OK;
+}
+
+static int need_comm(urh_ctx* ctx) {
+    if (!ctx->nccl_comm) URH_FAIL(ctx, URH_ERR_INVALID, "NCCL communicator not initialised (urh_nccl_init)");
+    return URH_OK;
+}
+
+// in-place all-reduce on device memory; op: 0 sum, 1 max, 2 min
+extern "C" int urh_nccl_allreduce_f64(urh_ctx* ctx, double* d_buf, int64_t count, int op) {
+    URH_CHECK(need_comm(ctx));
+    const int o = op == 0 ? URH_NCCL_SUM : (op == 1 ? URH_NCCL_MAX : URH_NCCL_MIN);
+    URH_NCCL(ctx, g_nccl.AllReduce(d_buf, d_buf, (size_t)count, URH_NCCL_FLOAT64, o, (urh_ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return URH_OK;
+}
+extern "C" int urh_nccl_allreduce_i64(urh_ctx* ctx, int64_t* d_buf, int64_t count, int op) {
+    URH_CHECK(need_comm(ctx));
+    const int o = op == 0 ? URH_NCCL_SUM : (op == 1 ? URH_NCCL_MAX : URH_NCCL_MIN);
+    URH_NCCL(ctx, g_nccl.AllReduce(d_buf, d_buf, (size_t)count, URH_NCCL_INT64, o, (urh_ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return URH_OK;
+}
+// d_recv holds world * bytes_per_rank bytes
+extern "C" int urh_nccl_allgather(urh_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank) {
+    URH_CHECK(need_comm(ctx));
+    URH_NCCL(ctx, g_nccl.AllGather(d_send, d_recv, bytes_per_rank, URH_NCCL_UINT8, (urh_ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return URH_OK;
+}
+// variable-length gather to `root`: h_bytes[world] are the per-rank byte counts (known to every rank);
+// root receives rank r's block at d_recv + sum(h_bytes[0..r))
+extern "C" int urh_nccl_gatherv(urh_ctx* ctx, const void* d_send, void* d_recv, const int64_t* h_bytes, int root) {
+    URH_CHECK(need_comm(ctx));
+    urh_ncclComm_t comm = (urh_ncclComm_t)ctx->nccl_comm;
+    URH_NCCL(ctx, g_nccl.GroupStart());
+    if (ctx->nccl_rank == root) {
+        int64_t off = 0;
+        for (int r = 0; r < ctx->nccl_world; r++) {
+            if (r == root) {
+                if (h_bytes[r] > 0) cudaMemcpyAsync((char*)d_recv + off, d_send, (size_t)h_bytes[r], cudaMemcpyDeviceToDevice, ctx->stream);
+            } else if (h_bytes[r] > 0) {
+                g_nccl.Recv((char*)d_recv + off, (size_t)h_bytes[r], URH_NCCL_UINT8, r, comm, ctx->stream);
+            }
+            off += h_bytes[r];
+        }
+    } else if (h_bytes[ctx->nccl_rank] > 0) {
+        g_nccl.Send(d_send, (size_t)h_bytes[ctx->nccl_rank], URH_NCCL_UINT8, root, comm, ctx->stream);
+    }
+    URH_NCCL(ctx, g_nccl.GroupEnd());
+    return URH_OK;
+}

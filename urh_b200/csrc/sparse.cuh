@@ -17,6 +17,19 @@ struct UrhCandidates {
 int urh_collect_candidates(urh_ctx* ctx, int64_t n, int tol, const UrhTileSummary* tiles, const uint32_t* staging,
                            int stage_cap, UrhCandidates* out);
 
+// Sharded captures: the run that ends at the end of the PRECEDING shards (class, length); valid = 0 for the first shard.
+struct UrhShardCarry {
+    int valid;
+    int cls;
+    int64_t len;
+};
+// As urh_collect_candidates, with the carry of the preceding shards folded in and positions offset by
+// `global_offset` (the shard's first sample index in the whole capture).
+int urh_collect_candidates_shard(urh_ctx* ctx, int64_t n, int tol, const UrhTileSummary* tiles, const uint32_t* staging,
+                                 int stage_cap, UrhShardCarry carry_in, int64_t global_offset, UrhCandidates* out);
+// The shard's own run summary for the exchange: h_out = {last_cls, last_len, whole (1 if the shard is one run)}.
+int urh_shard_run_total(urh_ctx* ctx, int64_t n, const UrhTileSummary* tiles, int64_t* h_out);
+
 // grab_pulse_lens tail (signal_functions.pyx:455-495) on the candidate table: fire filter, pulse lengths,
 // ASK short-pause relabel, merge of equal neighbours, tail row.  Result -> ctx->pulses / ctx->pulses_k.
 int urh_pulses_from_candidates(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t sps, const UrhCandidates& cand,

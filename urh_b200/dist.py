@@ -1,0 +1,186 @@
+"""One capture sharded by contiguous sample range over the GPUs of one box.
+
+One process per GPU (launched by torchrun).  ``torch.distributed`` (gloo) is the launcher plumbing: rendezvous and
+the exchange of tiny host-side descriptors; the data path between GPUs is NCCL over NVLink, driven from
+liburh_b200 (nccl.cu): the 1-sample halo, the all-reduce of the global noise statistics and the gather of the
+sparse candidate tables.  Per rank the sample-rate work is exactly the single-GPU dense pass.
+
+Protocol of the sharded digitizer (exactness argument in DESIGN.md §6):
+  1. every rank: dense pass over its shard (+1 halo sample for the FSK conjugate product) -> tile table and the
+     summary (class, length, whole?) of the run that closes the shard;
+  2. all-gather the summaries; rank r folds those of ranks < r with the run-carry operator -> the run that ends
+     right before its shard;
+  3. every rank: candidate table with global positions (the carry only affects the first run of the shard);
+  4. gather the candidate tables on rank 0 (NCCL send/recv), which finishes exactly like the single-GPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .device import DeviceArray
+
+
+# ---- pure host logic (unit-tested on CPU with gloo, tests/test_dist_cpu.py) -----------------------------------------
+def fold_carry(summaries):
+    """summaries: list of (last_cls, last_len, whole) per rank, in rank order.
+    Returns for every rank the run that ends right before its shard: None for rank 0, else (cls, len)."""
+    out = []
+    carry = None  # (cls, len, whole)
+    for cls, length, whole in summaries:
+        out.append(None if carry is None else (carry[0], carry[1]))
+        if carry is not None and whole and cls == carry[0]:
+            carry = (cls, carry[1] + length, carry[2])
+        else:
+            carry = (cls, length, bool(whole) and carry is None)
+    return out
+
+
+def shard_bounds(n_total: int, world: int, align: int = 2048):
+    """contiguous shards whose boundaries are multiples of `align` (the dense pass's tile), last one takes the rest"""
+    per = (n_total // world) // align * align
+    if per == 0:
+        per = n_total
+    bounds = []
+    start = 0
+    for r in range(world):
+        end = n_total if r == world - 1 else min(n_total, start + per)
+        bounds.append((start, end))
+        start = end
+    return bounds
+
+
+def combine_noise_chunks(n_total, chunksize, nchunks, partial_sums, partial_maxs):
+    """Global end-aligned noise chunks (AutoInterpretation.py:66-72) from per-rank partial (sum, max) arrays that were
+    all-reduced element-wise (sum / max) — identity here; kept for symmetry with the CPU test."""
+    return np.asarray(partial_sums, dtype=np.float64), np.asarray(partial_maxs, dtype=np.float64)
+
+
+class HostExchange(object):
+    """tiny host-side collectives over torch.distributed (gloo)"""
+
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+
+    def allgather(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def broadcast(self, obj, src=0):
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=src)
+        return box[0]
+
+    def barrier(self):
+        self.dist.barrier()
+
+
+def init_nccl(ctx: _lib.Context, hx: HostExchange):
+    """create the NCCL communicator of liburh_b200 for this context (id from rank 0 via the host exchange)"""
+    buf = C.create_string_buffer(128)
+    if hx.rank == 0:
+        rc = ctx.lib.urh_nccl_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError("urh_nccl_unique_id failed (libnccl.so.2 not loadable?)")
+    ident = hx.broadcast(bytes(buf.raw) if hx.rank == 0 else None, src=0)
+    ctx.check(ctx.lib.urh_nccl_init(ctx.handle, C.c_char_p(ident), hx.rank, hx.world))
+
+
+class ShardBuffer(object):
+    """Device buffer [pad][halo][shard samples...]: the shard starts 16-byte aligned, the halo sample sits right before it."""
+
+    def __init__(self, ctx, n_local, dtype=np.float32):
+        self.ctx = ctx
+        self.n = int(n_local)
+        self.dtype = np.dtype(dtype)
+        self.pad = max(1, 16 // (2 * self.dtype.itemsize))  # samples before the shard (>= 1 halo, keeps alignment)
+        self.buf = DeviceArray(ctx, (self.n + self.pad, 2), self.dtype)
+        self.shard = self.buf[self.pad:]
+        self.halo = self.buf[self.pad - 1: self.pad]
+
+
+def exchange_halo(ctx, hx, sb: ShardBuffer):
+    """rank r receives the last sample of rank r-1's shard (NCCL all-gather of one sample per rank)"""
+    one = sb.shard[sb.n - 1: sb.n]
+    allv = DeviceArray(ctx, (hx.world, 2), sb.dtype)
+    ctx.check(ctx.lib.urh_nccl_allgather(ctx.handle, C.c_void_p(one.ptr), C.c_void_p(allv.ptr), one.nbytes))
+    if hx.rank > 0:
+        src = allv[hx.rank - 1: hx.rank]
+        ctx.check(ctx.lib.urh_memcpy_d2d(ctx.handle, C.c_void_p(sb.halo.ptr), C.c_void_p(src.ptr), src.nbytes))
+    ctx.sync()
+
+
+def demod_digitize_sharded(ctx, hx, sb: ShardBuffer, global_offset, n_total, noise_mag, mod_type, center, tolerance,
+                           samples_per_symbol, bits_per_symbol=1, center_spacing=0.1, d_qad=None, root=0):
+    """FSK/ASK demod + digitize of a capture sharded over the ranks.  Returns the (k,2) pulse table on `root`
+    (None elsewhere).  `d_qad` (optional DeviceArray[n_local]) receives this rank's demodulated samples."""
+    lib = ctx.lib
+    code = _lib.demod_mod_code(mod_type)
+    summary = (C.c_int64 * 4)()
+    ctx.check(lib.urh_shard_dense(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, int(hx.rank > 0),
+                                  float(noise_mag), code, float(center), int(tolerance), int(bits_per_symbol), float(center_spacing),
+                                  C.c_void_p(d_qad.ptr if d_qad is not None else 0), summary))
+    mine = (int(summary[0]), int(summary[1]), int(summary[2]), int(summary[3]))
+    every = hx.allgather(mine)
+    carry = fold_carry([(c, l, w) for c, l, w, _ in every])[hx.rank]
+    count = C.c_int64(0)
+    d_pos, d_cls = C.c_void_p(), C.c_void_p()
+    ctx.check(lib.urh_shard_candidates(ctx.handle, int(carry is not None), carry[0] if carry else 0, carry[1] if carry else 0,
+                                       int(global_offset), C.byref(count), C.byref(d_pos), C.byref(d_cls)))
+    counts = hx.allgather(int(count.value))
+    total = int(sum(counts))
+    pos_all = cls_all = None
+    if hx.rank == root:
+        pos_all = DeviceArray(ctx, (max(total, 1),), np.int64)
+        cls_all = DeviceArray(ctx, (max(total, 1),), np.int16)
+    b8 = (C.c_int64 * hx.world)(*[c * 8 for c in counts])
+    b2 = (C.c_int64 * hx.world)(*[c * 2 for c in counts])
+    ctx.check(lib.urh_nccl_gatherv(ctx.handle, d_pos, C.c_void_p(pos_all.ptr if pos_all else 0), b8, root))
+    ctx.check(lib.urh_nccl_gatherv(ctx.handle, d_cls, C.c_void_p(cls_all.ptr if cls_all else 0), b2, root))
+    if hx.rank != root:
+        ctx.sync()
+        return None
+    k = C.c_int64(0)
+    ctx.check(lib.urh_pulses_from_table(ctx.handle, C.c_void_p(pos_all.ptr), C.c_void_p(cls_all.ptr), total, int(n_total),
+                                        int(tolerance), code, int(samples_per_symbol), every[0][3], C.byref(k)))
+    rows = np.empty((k.value, 2), dtype=np.int64)
+    if k.value:
+        ctx.check(lib.urh_fetch_pulses(ctx.handle, rows.ctypes.data_as(C.c_void_p), k.value))
+    return rows
+
+
+def detect_noise_level_sharded(ctx, hx, sb: ShardBuffer, global_offset, n_total):
+    """AutoInterpretation.detect_noise_level over the whole capture: per-rank partial (sum, max) of the 100 global,
+    end-aligned chunks, ONE NCCL all-reduce (sum half / max half share a buffer: max via sum of ... two calls), then
+    the reference's host logic."""
+    from .ainterpretation import AutoInterpretation as AI
+
+    if n_total <= 3:
+        return 0
+    chunksize, nchunks = AI._chunking(n_total)
+    # global chunk j covers [n_total-(j+1)*cs, n_total-j*cs); intersect with this shard
+    sums = np.zeros(nchunks, dtype=np.float64)
+    maxs = np.full(nchunks, -1.0, dtype=np.float64)
+    lo, hi = int(global_offset), int(global_offset) + sb.n
+    for j in range(nchunks):
+        c0, c1 = n_total - (j + 1) * chunksize, n_total - j * chunksize
+        a, b = max(c0, lo), min(c1, hi)
+        if a >= b:
+            if c1 <= lo:
+                break
+            continue
+        part = sb.shard[a - lo: b - lo]
+        s1, m1 = np.zeros(1), np.zeros(1)
+        ctx.check(ctx.lib.urh_noise_chunk_stats_iq(ctx.handle, C.c_void_p(part.ptr), _lib.dtype_code(sb.dtype), b - a, b - a, 1,
+                                                   s1.ctypes.data_as(C.c_void_p), m1.ctypes.data_as(C.c_void_p)))
+        sums[j], maxs[j] = s1[0], m1[0]
+    d_s = DeviceArray(ctx, (nchunks,), np.float64).set(sums)
+    d_m = DeviceArray(ctx, (nchunks,), np.float64).set(maxs)
+    ctx.check(ctx.lib.urh_nccl_allreduce_f64(ctx.handle, C.c_void_p(d_s.ptr), nchunks, 0))
+    ctx.check(ctx.lib.urh_nccl_allreduce_f64(ctx.handle, C.c_void_p(d_m.ptr), nchunks, 1))
+    return AI._noise_from_chunk_stats(n_total, chunksize, d_s.get(), d_m.get(), np.float64)
