@@ -149,7 +149,11 @@ int urh_shard_dense(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int ha
                     float center, uint16_t tolerance, uint8_t bits_per_symbol, float center_spacing, float* d_qad_out,
                     int64_t* h_summary);
 int urh_shard_candidates(urh_ctx* ctx, int carry_valid, int carry_cls, int64_t carry_len, int64_t global_offset,
-                         int64_t* count, const int64_t** d_pos, const int16_t** d_cls);
+                         int64_t* count, const int64_t** d_pos, const int16_t** d_cls, int* last_cand_cls);
+/* distributed finish (no gather): every rank keeps its own rows; see urh_b200/dist.py for the two scalars exchanged */
+int urh_shard_fire(urh_ctx* ctx, int prev_cls, int64_t* fired, int64_t* last_fired_pos);
+int urh_shard_rows(urh_ctx* ctx, int64_t n_total, uint16_t tolerance, int mod_type, uint32_t samples_per_symbol,
+                   int64_t prev_fired_pos, int emit_tail, int64_t* k);
 int urh_pulses_from_table(urh_ctx* ctx, const int64_t* d_pos, const int16_t* d_cls, int64_t count, int64_t n_total,
                           uint16_t tolerance, int mod_type, uint32_t samples_per_symbol, int init_cls, int64_t* k);
 /* NCCL (dlopen'ed libnccl.so.2): id from rank 0 is distributed by the launcher plumbing */
@@ -160,6 +164,7 @@ int urh_nccl_allreduce_f64(urh_ctx* ctx, double* d_buf, int64_t count, int op); 
 int urh_nccl_allreduce_i64(urh_ctx* ctx, int64_t* d_buf, int64_t count, int op);
 int urh_nccl_allgather(urh_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
 int urh_nccl_gatherv(urh_ctx* ctx, const void* d_send, void* d_recv, const int64_t* h_bytes, int root);
+int urh_nccl_allgather_host(urh_ctx* ctx, const void* h_send, void* h_recv, size_t bytes_per_rank);
 
 /* ---- measurement utilities (not part of the reference's API surface) -------------------------------- */
 /* CUDA-event timing of the dominant (dense, sample-rate) kernel of the last demod/digitize call */

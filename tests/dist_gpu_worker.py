@@ -42,6 +42,8 @@ def main():
         d_qad = DeviceArray(ctx, (hi - lo,), np.float32)
         rows = udist.demod_digitize_sharded(ctx, hx, sb, lo, n, noise, mod, center, tol, sps, d_qad=d_qad)
         qads = hx.allgather(d_qad.get())
+        part = udist.demod_digitize_distributed(ctx, rank, world, sb, lo, n, noise, mod, center, tol, sps)
+        parts = hx.allgather(part)
         noise_sh = udist.detect_noise_level_sharded(ctx, hx, sb, lo, n)
         if rank == 0:
             qad_ref, rows_ref = sf.demod_digitize(iq, noise, mod, center, tol, sps)
@@ -49,6 +51,8 @@ def main():
                 failures.append(("qad", case))
             if not np.array_equal(rows, rows_ref):
                 failures.append(("rows", case, len(rows), len(rows_ref)))
+            if not np.array_equal(udist.merge_shard_rows(parts), rows_ref):
+                failures.append(("rows_distributed", case))
             if noise_sh != AI.detect_noise_level_iq(iq):
                 failures.append(("noise", case, noise_sh))
     res = hx.allgather(failures)

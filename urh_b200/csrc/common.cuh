@@ -51,8 +51,10 @@ struct urh_ctx {
     void* shard_staging;
     int shard_cap, shard_tol;
     int64_t shard_n;
+    void* shard_state;
     // NCCL (nccl.cu)
     void* nccl_comm;
+    void* nccl_stage;
     int nccl_rank, nccl_world;
 };
 

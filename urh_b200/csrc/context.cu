@@ -29,7 +29,9 @@ extern "C" int urh_ctx_create(int device, urh_ctx** out) {
     ctx->fft_valid = false;
     ctx->shard_tiles = nullptr;
     ctx->shard_staging = nullptr;
+    ctx->shard_state = nullptr;
     ctx->nccl_comm = nullptr;
+    ctx->nccl_stage = nullptr;
     ctx->nccl_rank = 0;
     ctx->nccl_world = 1;
     if (cudaSetDevice(device) != cudaSuccess) {
@@ -68,6 +70,7 @@ extern "C" void urh_ctx_destroy(urh_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->arena) cudaFree(b.ptr);
     if (ctx->pulses) cudaFree(ctx->pulses);
+    if (ctx->shard_state) free(ctx->shard_state);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     for (int i = 0; i < 2; i++)
         if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);

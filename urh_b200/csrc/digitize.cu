@@ -374,21 +374,62 @@ extern "C" int urh_shard_dense(urh_ctx* ctx, const void* d_iq, int dtype, int64_
     return URH_OK;
 }
 
+struct UrhShardState {
+    UrhCandidates cand;
+    UrhFireState fs;
+    int16_t* d_prev;
+};
+static UrhShardState* shard_state(urh_ctx* ctx) {
+    if (!ctx->shard_state) ctx->shard_state = calloc(1, sizeof(UrhShardState));
+    return (UrhShardState*)ctx->shard_state;
+}
+
 // Step 2 on every rank, after the summaries were exchanged: carry_* describe the run that ends right before this
 // shard (fold of the preceding shards' summaries; carry_valid = 0 on the first shard).  Positions are global.
+// *last_cand_cls = class of the shard's last candidate (meaningful when *count > 0).
 extern "C" int urh_shard_candidates(urh_ctx* ctx, int carry_valid, int carry_cls, int64_t carry_len, int64_t global_offset,
-                                    int64_t* count, const int64_t** d_pos, const int16_t** d_cls) {
+                                    int64_t* count, const int64_t** d_pos, const int16_t** d_cls, int* last_cand_cls) {
     if (!ctx->shard_tiles) URH_FAIL(ctx, URH_ERR_INVALID, "urh_shard_dense must precede urh_shard_candidates");
     UrhShardCarry in;
     in.valid = carry_valid; in.cls = carry_cls; in.len = carry_len;
-    UrhCandidates cand;
+    UrhShardState* S = shard_state(ctx);
     URH_CHECK(urh_collect_candidates_shard(ctx, ctx->shard_n, ctx->shard_tol, (const UrhTileSummary*)ctx->shard_tiles,
-                                           (const uint32_t*)ctx->shard_staging, ctx->shard_cap, in, global_offset, &cand));
-    *count = cand.count;
-    if (d_pos) *d_pos = cand.pos;
-    if (d_cls) *d_cls = cand.cls;
+                                           (const uint32_t*)ctx->shard_staging, ctx->shard_cap, in, global_offset, &S->cand));
+    *count = S->cand.count;
+    if (d_pos) *d_pos = S->cand.pos;
+    if (d_cls) *d_cls = S->cand.cls;
+    if (last_cand_cls) {
+        *last_cand_cls = 0;
+        if (S->cand.count > 0) {
+            int16_t v = 0;
+            URH_CUDA(ctx, cudaMemcpyAsync(&v, S->cand.cls + S->cand.count - 1, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+            URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            *last_cand_cls = v;
+        }
+    }
     ctx->shard_tiles = nullptr;
     return URH_OK;
+}
+
+// Step 3 (distributed finish): prev_cls = class of the last candidate of the preceding shards (the digitizer's
+// initial state on the first shard).  Returns the number of firings and the position of the last one (-1: none).
+extern "C" int urh_shard_fire(urh_ctx* ctx, int prev_cls, int64_t* fired, int64_t* last_fired_pos) {
+    UrhShardState* S = shard_state(ctx);
+    URH_CHECK(urh_arena(ctx, 8, &S->d_prev));
+    const int16_t v = (int16_t)prev_cls;
+    URH_CUDA(ctx, cudaMemcpyAsync(S->d_prev, &v, sizeof(v), cudaMemcpyHostToDevice, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    URH_CHECK(urh_fire_stage(ctx, S->cand, S->d_prev, &S->fs, last_fired_pos));
+    *fired = S->fs.F;
+    return URH_OK;
+}
+
+// Step 4: this shard's rows (merged locally; equal states across a shard edge are merged by the consumer).
+// prev_fired_pos = position of the last firing in the preceding shards (-1: none); emit_tail on the last shard only.
+extern "C" int urh_shard_rows(urh_ctx* ctx, int64_t n_total, uint16_t tolerance, int mod_type, uint32_t samples_per_symbol,
+                              int64_t prev_fired_pos, int emit_tail, int64_t* k) {
+    UrhShardState* S = shard_state(ctx);
+    return urh_rows_stage(ctx, S->fs, n_total, tolerance, mod_type == URH_MOD_ASK, samples_per_symbol, prev_fired_pos, emit_tail != 0, k);
 }
 
 // Step 3 on the gathering rank: the concatenated candidate tables of all shards -> pulse table of the whole capture.

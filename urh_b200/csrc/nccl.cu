@@ -152,3 +152,19 @@ extern "C" int urh_nccl_gatherv(urh_ctx* ctx, const void* d_send, void* d_recv, 
     URH_NCCL(ctx, g_nccl.GroupEnd());
     return URH_OK;
 }
+
+// all-gather of a few host bytes per rank through a device staging buffer (metadata of the sharded digitizer:
+// cheaper than a TCP round trip through the launcher's process group)
+extern "C" int urh_nccl_allgather_host(urh_ctx* ctx, const void* h_send, void* h_recv, size_t bytes_per_rank) {
+    URH_CHECK(need_comm(ctx));
+    if (!ctx->nccl_stage) URH_CUDA(ctx, cudaMalloc(&ctx->nccl_stage, 65536));
+    const size_t total = bytes_per_rank * (size_t)ctx->nccl_world;
+    if (bytes_per_rank + total > 65536) URH_FAIL(ctx, URH_ERR_INVALID, "allgather_host: payload too large");
+    char* d_send = (char*)ctx->nccl_stage;
+    char* d_recv = d_send + ((bytes_per_rank + 255) & ~(size_t)255);
+    URH_CUDA(ctx, cudaMemcpyAsync(d_send, h_send, bytes_per_rank, cudaMemcpyHostToDevice, ctx->stream));
+    URH_NCCL(ctx, g_nccl.AllGather(d_send, d_recv, bytes_per_rank, URH_NCCL_UINT8, (urh_ncclComm_t)ctx->nccl_comm, ctx->stream));
+    URH_CUDA(ctx, cudaMemcpyAsync(h_recv, d_recv, total, cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return URH_OK;
+}

@@ -34,3 +34,18 @@ int urh_shard_run_total(urh_ctx* ctx, int64_t n, const UrhTileSummary* tiles, in
 // ASK short-pause relabel, merge of equal neighbours, tail row.  Result -> ctx->pulses / ctx->pulses_k.
 int urh_pulses_from_candidates(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t sps, const UrhCandidates& cand,
                                const int16_t* d_init_cls, int64_t* k);
+
+// The two halves of urh_pulses_from_candidates, separable so that shards can exchange the two scalars each half
+// needs from its predecessors: the class of the last candidate before the shard (fire decision of its first
+// candidate) and the position of the last firing before the shard (length of its first pulse).
+struct UrhFireState {
+    int64_t C, F;
+    int64_t* fire;
+    const int64_t* pos;
+    const int16_t* cls;
+    const int16_t* d_prev_cls;
+    int64_t *fpos, *st, *ln, *head;
+};
+int urh_fire_stage(urh_ctx* ctx, const UrhCandidates& cand, const int16_t* d_prev_cls, UrhFireState* fs, int64_t* last_fired_pos);
+int urh_rows_stage(urh_ctx* ctx, const UrhFireState& fs, int64_t n, int tol, bool is_ask, uint32_t sps, int64_t prev_fired,
+                   bool emit_tail, int64_t* k);

@@ -131,7 +131,7 @@ def demod_digitize_sharded(ctx, hx, sb: ShardBuffer, global_offset, n_total, noi
     count = C.c_int64(0)
     d_pos, d_cls = C.c_void_p(), C.c_void_p()
     ctx.check(lib.urh_shard_candidates(ctx.handle, int(carry is not None), carry[0] if carry else 0, carry[1] if carry else 0,
-                                       int(global_offset), C.byref(count), C.byref(d_pos), C.byref(d_cls)))
+                                       int(global_offset), C.byref(count), C.byref(d_pos), C.byref(d_cls), None))
     counts = hx.allgather(int(count.value))
     total = int(sum(counts))
     pos_all = cls_all = None
@@ -152,6 +152,73 @@ def demod_digitize_sharded(ctx, hx, sb: ShardBuffer, global_offset, n_total, noi
     if k.value:
         ctx.check(lib.urh_fetch_pulses(ctx.handle, rows.ctypes.data_as(C.c_void_p), k.value))
     return rows
+
+
+def nccl_allgather_i64(ctx, world, values):
+    """all-gather a few int64 per rank over NCCL (device-staged, ~tens of microseconds) -> array [world, len(values)]"""
+    send = np.ascontiguousarray(values, dtype=np.int64)
+    recv = np.empty((world, len(send)), dtype=np.int64)
+    ctx.check(ctx.lib.urh_nccl_allgather_host(ctx.handle, send.ctypes.data_as(C.c_void_p), recv.ctypes.data_as(C.c_void_p), send.nbytes))
+    return recv
+
+
+def previous_nonempty(values, counts, rank, default):
+    """value of the nearest rank < `rank` whose count is non-zero, else `default`"""
+    for r in range(rank - 1, -1, -1):
+        if counts[r] > 0:
+            return values[r]
+    return default
+
+
+def demod_digitize_distributed(ctx, rank, world, sb: ShardBuffer, global_offset, n_total, noise_mag, mod_type, center, tolerance,
+                               samples_per_symbol, bits_per_symbol=1, center_spacing=0.1, d_qad=None, fetch=True):
+    """Sharded FSK/ASK demod + digitize with a DISTRIBUTED finish: no gather, every rank ends with the rows of its own
+    shard (``merge_shard_rows`` joins them).  Three NCCL all-gathers of a few int64 per rank are the whole exchange:
+      (last_cls, last_len, whole, init_cls)  ->  run carry into the shard;
+      (candidate count, class of the last candidate)  ->  fire decision of the shard's first candidate;
+      (firing count, position of the last firing)  ->  length of the shard's first pulse."""
+    lib = ctx.lib
+    code = _lib.demod_mod_code(mod_type)
+    summary = (C.c_int64 * 4)()
+    ctx.check(lib.urh_shard_dense(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, int(rank > 0),
+                                  float(noise_mag), code, float(center), int(tolerance), int(bits_per_symbol), float(center_spacing),
+                                  C.c_void_p(d_qad.ptr if d_qad is not None else 0), summary))
+    every = nccl_allgather_i64(ctx, world, list(summary))
+    carry = fold_carry([(int(c), int(l), int(w)) for c, l, w, _ in every])[rank]
+    init_cls = int(every[0][3])
+    count, last_cls = C.c_int64(0), C.c_int(0)
+    ctx.check(lib.urh_shard_candidates(ctx.handle, int(carry is not None), carry[0] if carry else 0, carry[1] if carry else 0,
+                                       int(global_offset), C.byref(count), None, None, C.byref(last_cls)))
+    cc = nccl_allgather_i64(ctx, world, [count.value, last_cls.value])
+    prev_cls = int(previous_nonempty(cc[:, 1], cc[:, 0], rank, init_cls))
+    fired, last_pos = C.c_int64(0), C.c_int64(-1)
+    ctx.check(lib.urh_shard_fire(ctx.handle, prev_cls, C.byref(fired), C.byref(last_pos)))
+    ff = nccl_allgather_i64(ctx, world, [fired.value, last_pos.value])
+    prev_fired = int(previous_nonempty(ff[:, 1], ff[:, 0], rank, -1))
+    k = C.c_int64(0)
+    ctx.check(lib.urh_shard_rows(ctx.handle, int(n_total), int(tolerance), code, int(samples_per_symbol), prev_fired,
+                                 int(rank == world - 1), C.byref(k)))
+    if not fetch:
+        return int(k.value)
+    rows = np.empty((k.value, 2), dtype=np.int64)
+    if k.value:
+        ctx.check(lib.urh_fetch_pulses(ctx.handle, rows.ctypes.data_as(C.c_void_p), k.value))
+    return rows
+
+
+def merge_shard_rows(parts):
+    """concatenate per-shard pulse tables; equal states that meet at a shard edge are one pulse (pyx:475-476)"""
+    out = []
+    for rows in parts:
+        rows = np.asarray(rows, dtype=np.int64).reshape(-1, 2)
+        if len(rows) == 0:
+            continue
+        if out and out[-1][-1, 0] == rows[0, 0]:
+            out[-1][-1, 1] += rows[0, 1]
+            rows = rows[1:]
+        if len(rows):
+            out.append(rows.copy())
+    return np.concatenate(out) if out else np.zeros((0, 2), dtype=np.int64)
 
 
 def detect_noise_level_sharded(ctx, hx, sb: ShardBuffer, global_offset, n_total):
