@@ -109,7 +109,11 @@ def cpu_reference_arm(n_cpu, steps, warmup, iq_slice=None):
     from oracle import oracle, ref_loader
 
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun presets 1; the reference's prange should use every core
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(cores)  # in case libgomp is already loaded (torch)
+    except OSError:
+        pass
     kind = "port"
     demod, grab = oracle.afp_demod, oracle.grab_pulse_lens
     try:
@@ -156,7 +160,7 @@ def host_synth(n, seed=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=30, help="samples per GPU = 2**log2n (default 1 GiSample)")
@@ -169,7 +173,8 @@ def main():
     local_rank = env_int("LOCAL_RANK", 0)
     world = env_int("WORLD_SIZE", 1)
     n = 1 << args.log2n
-    workload = "2-FSK complex64 2^%d samples/GPU @2MS/s sps=100 +-20kHz AWGN sigma=0.01 bursts+gaps; demod+digitize (center=0, tol=5, noise=0.05)" % args.log2n
+    workload = ("2-FSK complex64, ONE capture of %d x 2^%d samples sharded by contiguous range (1-sample halo, NCCL run stitching) "
+                "@2MS/s sps=100 +-20kHz AWGN sigma=0.01 bursts+gaps; demod+digitize (center=0, tol=5, noise=0.05)" % (world, args.log2n))
     base = {"metric": "MSamples/s IQ demod+digitize (complex64)", "unit": "MSamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -201,21 +206,34 @@ def main():
     ctx = _lib.default_context(local_rank)
     lib = ctx.lib
     info = ctx.device_info()
+    n_total = n * world
+    offset = n * rank
 
-    # ---- synthesise this rank's capture directly in HBM ----------------------------------------------------
+    # ---- synthesise this rank's shard of ONE capture of world*2^log2n samples directly in HBM -------------------
+    # (N > 1: contiguous shards, 1-sample halo from the left neighbour over NCCL, run stitching as in urh_b200/dist.py)
+    from urh_b200 import dist as udist
+
     nsym = n // SPS + 2
     b, s = make_symbols(nsym, seed=1000 + rank)
     d_b = DeviceArray(ctx, (nsym,), np.int8).set(b)
     d_s = DeviceArray(ctx, (nsym,), np.int32).set(s)
-    d_iq = DeviceArray(ctx, (n, 2), np.float32)
+    sb = udist.ShardBuffer(ctx, n, np.float32)
+    d_iq = sb.shard
     d_qad = DeviceArray(ctx, (n,), np.float32)
     period, burst = 6_000_000, 5_000_000
-    ctx.check(lib.urh_synth_fsk(ctx.handle, C.c_void_p(d_iq.ptr), n, 0, SPS, C.c_void_p(d_b.ptr), C.c_void_p(d_s.ptr),
-                                C.c_double(FDEV / FS), 1.0, SIGMA, 12345 + rank, period, burst,
-                                int(0.40 * n), int(0.43 * n), int(0.97 * n)))
+    ctx.check(lib.urh_synth_fsk(ctx.handle, C.c_void_p(d_iq.ptr), n, offset, SPS, C.c_void_p(d_b.ptr), C.c_void_p(d_s.ptr),
+                                C.c_double(FDEV / FS), 1.0, SIGMA, 12345, period, burst,
+                                int(0.40 * n_total), int(0.43 * n_total), int(0.97 * n_total)))
     ctx.sync()
+    if world > 1:
+        hx = udist.HostExchange()
+        udist.init_nccl(ctx, hx)
+        udist.exchange_halo(ctx, hx, sb)
 
     def step_resident():
+        if world > 1:
+            return udist.demod_digitize_distributed(ctx, rank, world, sb, offset, n_total, NOISE_MAG, "FSK", CENTER, TOL, SPS,
+                                                    d_qad=d_qad, fetch=False)
         k = C.c_int64(0)
         ctx.check(lib.urh_demod_digitize(ctx.handle, C.c_void_p(d_iq.ptr), _lib.DT_F32, n, NOISE_MAG, _lib.MOD_FSK,
                                          CENTER, TOL, SPS, 1, 0.1, C.c_void_p(d_qad.ptr), C.byref(k)))
@@ -259,14 +277,23 @@ def main():
     e2e = None
     if not args.no_e2e:
         host = PinnedArray((n, 2), np.float32, ctx)
-        d_iq.get(out=host.array)  # the capture now lives in pinned host memory
-        d_e2e = DeviceArray(ctx, (n, 2), np.float32)
+        d_iq.get(out=host.array)  # this rank's shard now lives in pinned host memory
         e2e_steps = max(1, min(args.steps, 3))
+        if world > 1:
+            sb2 = udist.ShardBuffer(ctx, n, np.float32)
+            halo = sb.halo.get()
 
-        def step_e2e():
-            d_e2e.set_async(host.array)
-            qad, rows = sf.demod_digitize(d_e2e, NOISE_MAG, "FSK", CENTER, TOL, SPS, return_qad=False)
-            return rows
+            def step_e2e():
+                sb2.shard.set_async(host.array)
+                sb2.halo.set(halo)
+                return udist.demod_digitize_distributed(ctx, rank, world, sb2, offset, n_total, NOISE_MAG, "FSK", CENTER, TOL, SPS)
+        else:
+            d_e2e = DeviceArray(ctx, (n, 2), np.float32)
+
+            def step_e2e():
+                d_e2e.set_async(host.array)
+                qad, rows = sf.demod_digitize(d_e2e, NOISE_MAG, "FSK", CENTER, TOL, SPS, return_qad=False)
+                return rows
 
         rows = step_e2e()
         barrier()
@@ -287,6 +314,15 @@ def main():
                "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(rows.nbytes), "steps": e2e_steps,
                "api": "urh_b200.cythonext.signal_functions.demod_digitize(pinned host IQ) -> pulse table on host"}
         assert len(rows) == k_rows
+        # size-independent property of the digitizer: the pulse lengths of the whole capture sum to n_total - tolerance
+        lens = int(rows[:, 1].sum())
+        if dist is not None:
+            import torch
+
+            t = torch.tensor([lens], dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            lens = int(t.item())
+        assert lens == n_total - TOL, (lens, n_total - TOL)
         host.free()
 
     if rank != 0:
@@ -307,7 +343,7 @@ def main():
                 "kernel_share_of_step": dense / ms_per_step}
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         # bounded CPU sample of the same capture (first 2^cpu_log2n samples)
         ncpu = min(n, 1 << args.cpu_log2n)
         sl = d_iq[:ncpu].get()
