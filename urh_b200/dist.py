@@ -92,13 +92,14 @@ def init_nccl(ctx: _lib.Context, hx: HostExchange):
 
 
 class ShardBuffer(object):
-    """Device buffer [pad][halo][shard samples...]: the shard starts 16-byte aligned, the halo sample sits right before it."""
+    """Device buffer [pad][halo][shard samples...]: the shard starts 256-byte aligned (full-line warp loads), the halo
+    sample sits right before it."""
 
     def __init__(self, ctx, n_local, dtype=np.float32):
         self.ctx = ctx
         self.n = int(n_local)
         self.dtype = np.dtype(dtype)
-        self.pad = max(1, 16 // (2 * self.dtype.itemsize))  # samples before the shard (>= 1 halo, keeps alignment)
+        self.pad = 256 // (2 * self.dtype.itemsize)  # samples before the shard (>= 1 halo, keeps 256 B alignment)
         self.buf = DeviceArray(ctx, (self.n + self.pad, 2), self.dtype)
         self.shard = self.buf[self.pad:]
         self.halo = self.buf[self.pad - 1: self.pad]
