@@ -53,6 +53,7 @@ struct urh_ctx {
     int64_t shard_n;
     void* shard_state;
     // NCCL (nccl.cu)
+    int64_t costas_stats[3];
     void* nccl_comm;
     void* nccl_stage;
     int nccl_rank, nccl_world;

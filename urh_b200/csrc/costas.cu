@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(32) k_costas(const void* __restrict__ iq, int6
     }
 }
 
-int urh_costas_demod(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_sqrd, int loop_order,
-                     float bandwidth, float* d_out) {
+int urh_costas_demod_serial(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_sqrd, int loop_order,
+                            float bandwidth, float* d_out) {
     // signal_functions.pyx:252-287
     CostasParams P;
     const float damping = (float)(sqrt(2.0) / 2.0);

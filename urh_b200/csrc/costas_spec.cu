@@ -1,0 +1,294 @@
+// Speculative, chunk-parallel Costas loop — bit-identical to the serial recurrence of the reference
+// (signal_functions.pyx:252-330), SURVEY hard part H2.
+//
+// The PLL is contracting: two trajectories that sit in the same lock branch (phase offsets of 2*pi/order apart)
+// become BITWISE identical after a few hundred non-noise samples (measured on the CPU with glibc arithmetic:
+// >99 % of the starts inside a burst merge within 300 samples).  Hence:
+//   pass 1  (parallel: one thread per chunk and per branch candidate): start W samples before the chunk from the
+//           loop's initial state rotated by k*2*pi/order, run through the chunk, write the outputs to candidate
+//           buffer k and the loop state at every 256-sample checkpoint;
+//   pass 2  (one warp, chained): carry the TRUE state from chunk to chunk.  If it equals a candidate's state at the
+//           chunk start (bitwise), that candidate's run IS the true run for the whole chunk: O(1).  Otherwise step
+//           the true state serially through the chunk, segment by segment, until it meets a candidate checkpoint
+//           bitwise (typically ~300 samples after a burst starts); all-noise segments are skipped in O(1) because the
+//           loop state is frozen on noise samples (pyx:293-295) and every candidate holds NOISE there;
+//   pass 3  (parallel): assemble the result from the chosen candidate per segment.
+// Nothing is accepted on similarity: a candidate's samples are used only downstream of a bitwise state match, where
+// the deterministic recurrence guarantees identical results.  Worst case (never matching) degrades to the serial loop.
+#include "dense.cuh"
+#include "glibc_sincosf.h"
+
+#include <math.h>
+
+#define CS_CHUNK 4096
+#define CS_SEG 256
+#define CS_SEGS (CS_CHUNK / CS_SEG)
+#define CS_WARM 1024
+#define CS_MAXBR 4
+
+struct CsParams {
+    float noise_sqrd, alpha, beta, scale, shift;
+    int order;  // 2 or 4
+};
+
+struct __align__(8) CsState {
+    float freq, phase;
+};
+
+template <int DT>
+__device__ __forceinline__ void cs_load(const void* iq, int64_t i, float& re, float& im) {
+    typedef typename UrhElem<DT>::type E;
+    const E* p = (const E*)iq + 2 * i;
+    re = (float)p[0];
+    im = (float)p[1];
+}
+
+// one sample of the loop; returns true if the sample is above the noise gate (state advanced), out = result[i]
+__device__ __forceinline__ bool cs_step(CsState& s, float re, float im, const CsParams& P, float& out) {
+    if (__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)) <= P.noise_sqrd) {
+        out = -4.0f;
+        return false;
+    }
+    const float rf = __fdiv_rn(__fadd_rn(re, P.shift), P.scale);
+    const float jf = __fdiv_rn(__fadd_rn(im, P.shift), P.scale);
+    const float cs_r = __fadd_rn(rf, __fmul_rn(0.0f, jf));          // rf + (0*jf - 1*0)
+    const float cs_i = __fadd_rn(0.0f, __fadd_rn(0.0f, jf));
+    float sn, cn;
+    int ok;
+    urh_glibc_sincosf(-s.phase, &sn, &cn, &ok);
+    if (!ok) sincosf(-s.phase, &sn, &cn);
+    const float nr = __fadd_rn(cn, __fmul_rn(0.0f, sn));
+    const float ni = __fadd_rn(0.0f, __fadd_rn(0.0f, sn));
+    const float xr = __fsub_rn(__fmul_rn(nr, cs_r), __fmul_rn(ni, cs_i));
+    const float xi = __fadd_rn(__fmul_rn(nr, cs_i), __fmul_rn(ni, cs_r));
+    float err;
+    if (P.order == 2) err = __fmul_rn(xi, xr);
+    else {
+        const float f1 = xr > 0.0f ? 1.0f : -1.0f;
+        const float f2 = xi > 0.0f ? 1.0f : -1.0f;
+        err = __fsub_rn(__fmul_rn(f1, xi), __fmul_rn(f2, xr));
+    }
+    err = err < -1.0f ? -1.0f : (err > 1.0f ? 1.0f : err);
+    s.freq = __fadd_rn(s.freq, __fmul_rn(P.beta, err));
+    s.phase = __fadd_rn(s.phase, __fadd_rn(s.freq, __fmul_rn(P.alpha, err)));
+    const double two_pi = 2.0 * M_PI;
+    while ((double)s.phase > two_pi) s.phase = (float)((double)s.phase - two_pi);
+    while ((double)s.phase < -two_pi) s.phase = (float)((double)s.phase + two_pi);
+    s.freq = s.freq < -1.0f ? -1.0f : (s.freq > 1.0f ? 1.0f : s.freq);
+    out = (P.order == 2) ? xr : (float)(2.0 * (double)xr + (double)xi);
+    return true;
+}
+
+// pass 1: grid.x covers chunks, grid.y = candidate k
+template <int DT>
+__global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ iq, int64_t n, CsParams P, int64_t nchunks,
+                                                      float* __restrict__ cand, CsState* __restrict__ ckpt,
+                                                      int* __restrict__ nonnoise) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (c >= nchunks) return;
+    const int64_t p0 = c * CS_CHUNK;
+    float* out = cand + (int64_t)k * n;
+    CsState* ck = ckpt + ((int64_t)k * nchunks + c) * (CS_SEGS + 1);
+    CsState s;
+    s.freq = 0.0f;
+    // candidate k: the loop's initial phase 1.5 rotated by k * 2*pi/order (branch of the lock point)
+    s.phase = (float)(1.5 + (double)k * (2.0 * M_PI / (double)P.order));
+    if ((double)s.phase > 2.0 * M_PI) s.phase = (float)((double)s.phase - 2.0 * M_PI);
+    float o;
+    if (c == 0) {
+        if (k != 0) return;  // chunk 0 starts from the true initial state: one exact run only
+        s.phase = 1.5f;
+    } else {
+        int64_t w0 = p0 - CS_WARM;
+        if (w0 < 1) w0 = 1;
+        for (int64_t i = w0; i < p0; i++) {
+            float re, im;
+            cs_load<DT>(iq, i, re, im);
+            cs_step(s, re, im, P, o);
+        }
+    }
+    ck[0] = s;
+    for (int j = 0; j < CS_SEGS; j++) {
+        const int64_t a = p0 + (int64_t)j * CS_SEG;
+        int cnt = 0;
+        for (int64_t i = a; i < a + CS_SEG && i < n; i++) {
+            if (i == 0) { out[0] = 0.0f; continue; }  // the reference loop starts at i = 1 (result[0] undefined -> 0)
+            float re, im;
+            cs_load<DT>(iq, i, re, im);
+            cnt += cs_step(s, re, im, P, o) ? 1 : 0;
+            out[i] = o;
+        }
+        ck[j + 1] = s;
+        if (k == 0) nonnoise[c * CS_SEGS + j] = cnt;
+    }
+}
+
+// pass 2: the chain.  src[c*CS_SEGS + j]: candidate index whose samples are the true ones in that segment, or 255
+// when the resolver wrote the true samples itself.
+template <int DT>
+__global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, int64_t n, CsParams P, int64_t nchunks, int nbr,
+                                                   const CsState* __restrict__ ckpt, const int* __restrict__ nonnoise,
+                                                   float* __restrict__ out, uint8_t* __restrict__ src,
+                                                   int64_t* __restrict__ stats) {
+    const int lane = threadIdx.x;
+    // true state at the end of chunk 0 (exact run)
+    CsState st = ckpt[CS_SEGS];
+    if (lane < CS_SEGS) src[lane] = 0;
+    int64_t fast = 0, slow = 0, stepped = 0;
+    for (int64_t c0 = 1; c0 < nchunks; c0 += 32) {
+        // every lane prefetches the candidates' start/end states of chunk c0 + lane
+        const int64_t cl = c0 + lane;
+        CsState s0[CS_MAXBR], s1[CS_MAXBR];
+#pragma unroll
+        for (int k = 0; k < CS_MAXBR; k++) {
+            if (k < nbr && cl < nchunks) {
+                const CsState* ck = ckpt + ((int64_t)k * nchunks + cl) * (CS_SEGS + 1);
+                s0[k] = ck[0];
+                s1[k] = ck[CS_SEGS];
+            } else {
+                s0[k].freq = s0[k].phase = s1[k].freq = s1[k].phase = __int_as_float(0x7fc00000);
+            }
+        }
+        const int todo = (int)min((int64_t)32, nchunks - c0);
+        for (int t = 0; t < todo; t++) {
+            const int64_t c = c0 + t;
+            int match = -1;
+            CsState e;
+            e.freq = e.phase = 0.f;
+#pragma unroll
+            for (int k = 0; k < CS_MAXBR; k++) {
+                const float f0 = __shfl_sync(URH_FULL_MASK, s0[k].freq, t), p0 = __shfl_sync(URH_FULL_MASK, s0[k].phase, t);
+                const float f1 = __shfl_sync(URH_FULL_MASK, s1[k].freq, t), p1 = __shfl_sync(URH_FULL_MASK, s1[k].phase, t);
+                if (match < 0 && k < nbr && __float_as_uint(f0) == __float_as_uint(st.freq) &&
+                    __float_as_uint(p0) == __float_as_uint(st.phase)) {
+                    match = k;
+                    e.freq = f1;
+                    e.phase = p1;
+                }
+            }
+            if (match >= 0) {  // O(1): the candidate's run is the true run
+                if (lane < CS_SEGS) src[c * CS_SEGS + lane] = (uint8_t)match;
+                st = e;
+                fast++;
+                continue;
+            }
+            slow++;
+            // walk the chunk from the true state; lane 0 computes, the decision is broadcast
+            int merged = -1, jm = CS_SEGS;
+            for (int j = 0; j < CS_SEGS; j++) {
+                const int cnt = nonnoise[c * CS_SEGS + j];
+                if (cnt == 0) {  // state frozen, every candidate holds NOISE here
+                    if (lane == 0) src[c * CS_SEGS + j] = 0;
+                    continue;
+                }
+                const int64_t a = c * CS_CHUNK + (int64_t)j * CS_SEG;
+                if (lane == 0) {
+                    for (int64_t i = a; i < a + CS_SEG && i < n; i++) {
+                        float re, im, o;
+                        cs_load<DT>(iq, i, re, im);
+                        cs_step(st, re, im, P, o);
+                        out[i] = o;
+                    }
+                    src[c * CS_SEGS + j] = 255;
+                }
+                stepped += CS_SEG;
+                st.freq = __shfl_sync(URH_FULL_MASK, st.freq, 0);
+                st.phase = __shfl_sync(URH_FULL_MASK, st.phase, 0);
+                // does the true state now coincide with a candidate checkpoint?
+                int m = -1;
+                if (lane < nbr) {
+                    const CsState q = ckpt[((int64_t)lane * nchunks + c) * (CS_SEGS + 1) + j + 1];
+                    if (__float_as_uint(q.freq) == __float_as_uint(st.freq) && __float_as_uint(q.phase) == __float_as_uint(st.phase)) m = lane;
+                }
+                const unsigned any = __ballot_sync(URH_FULL_MASK, m >= 0);
+                if (any) {
+                    merged = __ffs(any) - 1;
+                    jm = j + 1;
+                    break;
+                }
+            }
+            if (merged >= 0) {
+                if (lane >= jm && lane < CS_SEGS) src[c * CS_SEGS + lane] = (uint8_t)merged;
+                const CsState q = ckpt[((int64_t)merged * nchunks + c) * (CS_SEGS + 1) + CS_SEGS];
+                st = q;
+            }
+        }
+    }
+    if (lane == 0 && stats) {
+        stats[0] = fast;
+        stats[1] = slow;
+        stats[2] = stepped;
+    }
+}
+
+// pass 3: out[i] = candidate[src][i] (segments the resolver wrote itself are left alone)
+__global__ void k_cs_assemble(const float* __restrict__ cand, int64_t n, const uint8_t* __restrict__ src, float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint8_t k = src[i / CS_SEG];
+        if (k != 255) out[i] = cand[(int64_t)k * n + i];
+    }
+}
+
+int urh_costas_demod_serial(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_sqrd, int loop_order,
+                            float bandwidth, float* d_out);  // costas.cu
+
+int urh_costas_demod(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_sqrd, int loop_order, float bandwidth,
+                     float* d_out) {
+    const int order = loop_order > 4 ? 4 : loop_order;  // pyx:285-287
+    if (n < 4 * CS_CHUNK || (order != 2 && order != 4))
+        return urh_costas_demod_serial(ctx, d_iq, dtype, n, noise_sqrd, loop_order, bandwidth, d_out);
+    CsParams P;
+    const float damping = (float)(sqrt(2.0) / 2.0);
+    const double bw = (double)bandwidth, dm = (double)damping;
+    volatile float bw2f = bandwidth * bandwidth;
+    const double den = (1.0 + ((2.0 * dm) * bw)) + (double)bw2f;
+    P.alpha = (float)(((4.0 * dm) * bw) / den);
+    P.beta = (float)(((4.0 * bw) * bw) / den);
+    P.noise_sqrd = noise_sqrd;
+    P.order = order;
+    switch (dtype) {
+        case URH_DT_I8: P.scale = 127.5f; P.shift = 0.5f; break;
+        case URH_DT_U8: P.scale = 127.5f; P.shift = -127.5f; break;
+        case URH_DT_I16: P.scale = 32767.5f; P.shift = 0.5f; break;
+        case URH_DT_U16: P.scale = 65535.0f; P.shift = -32767.5f; break;
+        case URH_DT_F32: P.scale = 1.0f; P.shift = 0.0f; break;
+        default: URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
+    }
+    urh_arena_reset(ctx);
+    const int64_t nchunks = urh_div_up(n, CS_CHUNK);
+    const int nbr = order;  // candidates = lock branches
+    float* cand;
+    CsState* ckpt;
+    int* nonnoise;
+    uint8_t* src;
+    int64_t* stats;
+    URH_CHECK(urh_arena(ctx, (size_t)nbr * n, &cand));
+    URH_CHECK(urh_arena(ctx, (size_t)nbr * nchunks * (CS_SEGS + 1), &ckpt));
+    URH_CHECK(urh_arena(ctx, (size_t)nchunks * CS_SEGS, &nonnoise));
+    URH_CHECK(urh_arena(ctx, (size_t)nchunks * CS_SEGS, &src));
+    URH_CHECK(urh_arena(ctx, 4, &stats));
+    const dim3 grid((unsigned)urh_div_up(nchunks, 128), (unsigned)nbr);
+    const unsigned ga = (unsigned)min(urh_div_up(n, 256), (int64_t)ctx->sm_count * 32);
+#define CS_RUN(DT)                                                                                                         \
+    URH_LAUNCH(ctx, k_cs_speculate<DT>, grid, 128, 0, d_iq, n, P, nchunks, cand, ckpt, nonnoise);                            \
+    URH_LAUNCH(ctx, k_cs_resolve<DT>, 1, 32, 0, d_iq, n, P, nchunks, nbr, ckpt, nonnoise, d_out, src, stats);
+    switch (dtype) {
+        case URH_DT_I8: CS_RUN(URH_DT_I8) break;
+        case URH_DT_U8: CS_RUN(URH_DT_U8) break;
+        case URH_DT_I16: CS_RUN(URH_DT_I16) break;
+        case URH_DT_U16: CS_RUN(URH_DT_U16) break;
+        default: CS_RUN(URH_DT_F32) break;
+    }
+#undef CS_RUN
+    URH_LAUNCH(ctx, k_cs_assemble, ga, 256, 0, cand, n, src, d_out);
+    URH_CHECK(urh_read_i64(ctx, stats, 3, ctx->costas_stats));
+    return URH_OK;
+}
+
+// diagnostics of the last speculative run: {chunks resolved in O(1), chunks walked, samples stepped serially}
+extern "C" int urh_costas_stats(urh_ctx* ctx, int64_t* h_out3) {
+    for (int i = 0; i < 3; i++) h_out3[i] = ctx->costas_stats[i];
+    return URH_OK;
+}
