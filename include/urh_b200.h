@@ -156,6 +156,11 @@ int urh_shard_rows(urh_ctx* ctx, int64_t n_total, uint16_t tolerance, int mod_ty
                    int64_t prev_fired_pos, int emit_tail, int64_t* k);
 int urh_pulses_from_table(urh_ctx* ctx, const int64_t* d_pos, const int16_t* d_cls, int64_t count, int64_t n_total,
                           uint16_t tolerance, int mod_type, uint32_t samples_per_symbol, int init_cls, int64_t* k);
+/* PSK (Costas loop) over shards: speculate concurrently on every rank, then hand the loop state from rank to rank */
+int urh_costas_halo_samples(void);
+int urh_costas_shard_speculate(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int first_shard, float noise_mag,
+                               int loop_order, float bandwidth, float* d_out);
+int urh_costas_shard_resolve(urh_ctx* ctx, const float* h_state_in, float* h_state_out);
 /* NCCL (dlopen'ed libnccl.so.2): id from rank 0 is distributed by the launcher plumbing */
 int urh_nccl_unique_id(char* out128);
 int urh_nccl_init(urh_ctx* ctx, const char* id128, int rank, int world);

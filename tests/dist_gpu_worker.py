@@ -55,6 +55,25 @@ def main():
                 failures.append(("rows_distributed", case))
             if noise_sh != AI.detect_noise_level_iq(iq):
                 failures.append(("noise", case, noise_sh))
+    # PSK: speculative Costas loop over shards == single-GPU == oracle (bit-exact)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_costas import synth_psk
+
+    for order in (2, 4):
+        n = 1_200_000
+        iq = synth_psk(n, order, seed=40 + order, gap_period=250000, gap_len=60000)
+        lo, hi = udist.shard_bounds(n, world)[rank]
+        sb = udist.ShardBuffer(ctx, hi - lo, np.float32, halo=udist.costas_halo(ctx))
+        sb.shard.set(iq[lo:hi])
+        udist.exchange_halo(ctx, hx, sb)
+        d_out = DeviceArray(ctx, (hi - lo,), np.float32)
+        udist.afp_demod_psk_sharded(ctx, rank, world, sb, 0.2, order, 0.1, d_out)
+        parts = hx.allgather(d_out.get())
+        if rank == 0:
+            ref = sf.afp_demod(iq, 0.2, "PSK", order)
+            got = np.concatenate(parts)
+            if not np.array_equal(got[1:].view(np.uint32), ref[1:].view(np.uint32)):
+                failures.append(("psk", order, int((got[1:].view(np.uint32) != ref[1:].view(np.uint32)).sum())))
     res = hx.allgather(failures)
     if rank == 0:
         flat = [f for part in res for f in part]

@@ -99,6 +99,9 @@ SIGNATURES = {
     "urh_shard_rows": (i32, [vp, i64, u16, i32, u32, i64, i32, C.POINTER(i64)]),
     "urh_nccl_allgather_host": (i32, [vp, vp, vp, szt]),
     "urh_pulses_from_table": (i32, [vp, vp, vp, i64, i64, u16, i32, u32, i32, C.POINTER(i64)]),
+    "urh_costas_halo_samples": (i32, []),
+    "urh_costas_shard_speculate": (i32, [vp, vp, i32, i64, i32, f32, i32, f32, vp]),
+    "urh_costas_shard_resolve": (i32, [vp, vp, vp]),
     "urh_nccl_unique_id": (i32, [vp]),
     "urh_nccl_init": (i32, [vp, vp, i32, i32]),
     "urh_nccl_destroy": (i32, [vp]),

@@ -83,7 +83,7 @@ __device__ __forceinline__ bool cs_step(CsState& s, float re, float im, const Cs
 template <int DT>
 __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ iq, int64_t n, CsParams P, int64_t nchunks,
                                                       float* __restrict__ cand, CsState* __restrict__ ckpt,
-                                                      int* __restrict__ nonnoise) {
+                                                      int* __restrict__ nonnoise, int first_shard) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (c >= nchunks) return;
@@ -96,12 +96,13 @@ __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ i
     s.phase = (float)(1.5 + (double)k * (2.0 * M_PI / (double)P.order));
     if ((double)s.phase > 2.0 * M_PI) s.phase = (float)((double)s.phase - 2.0 * M_PI);
     float o;
-    if (c == 0) {
-        if (k != 0) return;  // chunk 0 starts from the true initial state: one exact run only
+    if (c == 0 && first_shard) {
+        if (k != 0) return;  // chunk 0 of the capture starts from the true initial state: one exact run only
         s.phase = 1.5f;
     } else {
+        // later shards of a sharded capture have CS_WARM halo samples stored in front of iq (negative indices)
         int64_t w0 = p0 - CS_WARM;
-        if (w0 < 1) w0 = 1;
+        if (first_shard && w0 < 1) w0 = 1;
         for (int64_t i = w0; i < p0; i++) {
             float re, im;
             cs_load<DT>(iq, i, re, im);
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ i
         const int64_t a = p0 + (int64_t)j * CS_SEG;
         int cnt = 0;
         for (int64_t i = a; i < a + CS_SEG && i < n; i++) {
-            if (i == 0) { out[0] = 0.0f; continue; }  // the reference loop starts at i = 1 (result[0] undefined -> 0)
+            if (i == 0 && first_shard) { out[0] = 0.0f; continue; }  // the reference loop starts at i = 1 (result[0] undefined -> 0)
             float re, im;
             cs_load<DT>(iq, i, re, im);
             cnt += cs_step(s, re, im, P, o) ? 1 : 0;
@@ -130,13 +131,15 @@ template <int DT>
 __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, int64_t n, CsParams P, int64_t nchunks, int nbr,
                                                    const CsState* __restrict__ ckpt, const int* __restrict__ nonnoise,
                                                    float* __restrict__ out, uint8_t* __restrict__ src,
-                                                   int64_t* __restrict__ stats) {
+                                                   int64_t* __restrict__ stats, int first_shard, CsState st_in,
+                                                   CsState* __restrict__ st_out) {
     const int lane = threadIdx.x;
-    // true state at the end of chunk 0 (exact run)
-    CsState st = ckpt[CS_SEGS];
-    if (lane < CS_SEGS) src[lane] = 0;
+    // first shard: true state at the end of chunk 0 (exact run); later shards: the state handed over by the
+    // preceding shard, and chunk 0 is resolved like every other chunk
+    CsState st = first_shard ? ckpt[CS_SEGS] : st_in;
+    if (first_shard && lane < CS_SEGS) src[lane] = 0;
     int64_t fast = 0, slow = 0, stepped = 0;
-    for (int64_t c0 = 1; c0 < nchunks; c0 += 32) {
+    for (int64_t c0 = first_shard ? 1 : 0; c0 < nchunks; c0 += 32) {
         // every lane prefetches the candidates' start/end states of chunk c0 + lane
         const int64_t cl = c0 + lane;
         CsState s0[CS_MAXBR], s1[CS_MAXBR];
@@ -215,6 +218,7 @@ __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, 
             }
         }
     }
+    if (lane == 0 && st_out) *st_out = st;
     if (lane == 0 && stats) {
         stats[0] = fast;
         stats[1] = slow;
@@ -234,57 +238,118 @@ __global__ void k_cs_assemble(const float* __restrict__ cand, int64_t n, const u
 int urh_costas_demod_serial(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_sqrd, int loop_order,
                             float bandwidth, float* d_out);  // costas.cu
 
-int urh_costas_demod(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_sqrd, int loop_order, float bandwidth,
-                     float* d_out) {
-    const int order = loop_order > 4 ? 4 : loop_order;  // pyx:285-287
-    if (n < 4 * CS_CHUNK || (order != 2 && order != 4))
-        return urh_costas_demod_serial(ctx, d_iq, dtype, n, noise_sqrd, loop_order, bandwidth, d_out);
-    CsParams P;
+static int cs_params(urh_ctx* ctx, CsParams* P, int dtype, float noise_sqrd, int order, float bandwidth) {
     const float damping = (float)(sqrt(2.0) / 2.0);
     const double bw = (double)bandwidth, dm = (double)damping;
     volatile float bw2f = bandwidth * bandwidth;
     const double den = (1.0 + ((2.0 * dm) * bw)) + (double)bw2f;
-    P.alpha = (float)(((4.0 * dm) * bw) / den);
-    P.beta = (float)(((4.0 * bw) * bw) / den);
-    P.noise_sqrd = noise_sqrd;
-    P.order = order;
+    P->alpha = (float)(((4.0 * dm) * bw) / den);
+    P->beta = (float)(((4.0 * bw) * bw) / den);
+    P->noise_sqrd = noise_sqrd;
+    P->order = order;
     switch (dtype) {
-        case URH_DT_I8: P.scale = 127.5f; P.shift = 0.5f; break;
-        case URH_DT_U8: P.scale = 127.5f; P.shift = -127.5f; break;
-        case URH_DT_I16: P.scale = 32767.5f; P.shift = 0.5f; break;
-        case URH_DT_U16: P.scale = 65535.0f; P.shift = -32767.5f; break;
-        case URH_DT_F32: P.scale = 1.0f; P.shift = 0.0f; break;
+        case URH_DT_I8: P->scale = 127.5f; P->shift = 0.5f; break;
+        case URH_DT_U8: P->scale = 127.5f; P->shift = -127.5f; break;
+        case URH_DT_I16: P->scale = 32767.5f; P->shift = 0.5f; break;
+        case URH_DT_U16: P->scale = 65535.0f; P->shift = -32767.5f; break;
+        case URH_DT_F32: P->scale = 1.0f; P->shift = 0.0f; break;
         default: URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
     }
-    urh_arena_reset(ctx);
-    const int64_t nchunks = urh_div_up(n, CS_CHUNK);
-    const int nbr = order;  // candidates = lock branches
+    return URH_OK;
+}
+
+struct CsRun {
+    CsParams P;
+    const void* iq;
+    int dtype, nbr, first_shard;
+    int64_t n, nchunks;
     float* cand;
     CsState* ckpt;
     int* nonnoise;
     uint8_t* src;
     int64_t* stats;
-    URH_CHECK(urh_arena(ctx, (size_t)nbr * n, &cand));
-    URH_CHECK(urh_arena(ctx, (size_t)nbr * nchunks * (CS_SEGS + 1), &ckpt));
-    URH_CHECK(urh_arena(ctx, (size_t)nchunks * CS_SEGS, &nonnoise));
-    URH_CHECK(urh_arena(ctx, (size_t)nchunks * CS_SEGS, &src));
-    URH_CHECK(urh_arena(ctx, 4, &stats));
-    const dim3 grid((unsigned)urh_div_up(nchunks, 128), (unsigned)nbr);
-    const unsigned ga = (unsigned)min(urh_div_up(n, 256), (int64_t)ctx->sm_count * 32);
-#define CS_RUN(DT)                                                                                                         \
-    URH_LAUNCH(ctx, k_cs_speculate<DT>, grid, 128, 0, d_iq, n, P, nchunks, cand, ckpt, nonnoise);                            \
-    URH_LAUNCH(ctx, k_cs_resolve<DT>, 1, 32, 0, d_iq, n, P, nchunks, nbr, ckpt, nonnoise, d_out, src, stats);
-    switch (dtype) {
-        case URH_DT_I8: CS_RUN(URH_DT_I8) break;
-        case URH_DT_U8: CS_RUN(URH_DT_U8) break;
-        case URH_DT_I16: CS_RUN(URH_DT_I16) break;
-        case URH_DT_U16: CS_RUN(URH_DT_U16) break;
-        default: CS_RUN(URH_DT_F32) break;
+    CsState* st_out;
+    float* out;
+};
+
+static int cs_speculate(urh_ctx* ctx, CsRun& R) {
+    urh_arena_reset(ctx);
+    R.nchunks = urh_div_up(R.n, CS_CHUNK);
+    R.nbr = R.P.order;  // candidates = lock branches
+    URH_CHECK(urh_arena(ctx, (size_t)R.nbr * R.n, &R.cand));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nbr * R.nchunks * (CS_SEGS + 1), &R.ckpt));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nchunks * CS_SEGS, &R.nonnoise));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nchunks * CS_SEGS, &R.src));
+    URH_CHECK(urh_arena(ctx, 4, &R.stats));
+    URH_CHECK(urh_arena(ctx, 2, &R.st_out));
+    const dim3 grid((unsigned)urh_div_up(R.nchunks, 128), (unsigned)R.nbr);
+    switch (R.dtype) {
+        case URH_DT_I8: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_I8>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.first_shard); break;
+        case URH_DT_U8: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_U8>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.first_shard); break;
+        case URH_DT_I16: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_I16>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.first_shard); break;
+        case URH_DT_U16: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_U16>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.first_shard); break;
+        default: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_F32>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.first_shard); break;
     }
-#undef CS_RUN
-    URH_LAUNCH(ctx, k_cs_assemble, ga, 256, 0, cand, n, src, d_out);
-    URH_CHECK(urh_read_i64(ctx, stats, 3, ctx->costas_stats));
     return URH_OK;
+}
+
+static int cs_resolve(urh_ctx* ctx, CsRun& R, CsState st_in, float* h_state_out) {
+    switch (R.dtype) {
+        case URH_DT_I8: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_I8>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
+        case URH_DT_U8: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_U8>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
+        case URH_DT_I16: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_I16>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
+        case URH_DT_U16: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_U16>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
+        default: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_F32>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
+    }
+    const unsigned ga = (unsigned)min(urh_div_up(R.n, 256), (int64_t)ctx->sm_count * 32);
+    URH_LAUNCH(ctx, k_cs_assemble, ga, 256, 0, R.cand, R.n, R.src, R.out);
+    URH_CHECK(urh_read_i64(ctx, R.stats, 3, ctx->costas_stats));
+    if (h_state_out) {
+        URH_CUDA(ctx, cudaMemcpyAsync(h_state_out, R.st_out, sizeof(CsState), cudaMemcpyDeviceToHost, ctx->stream));
+        URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return URH_OK;
+}
+
+int urh_costas_demod(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_sqrd, int loop_order, float bandwidth,
+                     float* d_out) {
+    const int order = loop_order > 4 ? 4 : loop_order;  // pyx:285-287
+    if (n < 4 * CS_CHUNK || (order != 2 && order != 4))
+        return urh_costas_demod_serial(ctx, d_iq, dtype, n, noise_sqrd, loop_order, bandwidth, d_out);
+    CsRun R;
+    URH_CHECK(cs_params(ctx, &R.P, dtype, noise_sqrd, order, bandwidth));
+    R.iq = d_iq; R.dtype = dtype; R.n = n; R.first_shard = 1; R.out = d_out;
+    URH_CHECK(cs_speculate(ctx, R));
+    CsState none;
+    none.freq = 0.f; none.phase = 1.5f;
+    return cs_resolve(ctx, R, none, nullptr);
+}
+
+// ---- PSK captures sharded over GPUs: pass 1 runs concurrently on every rank, the chain is handed from rank to rank ----
+// d_iq points at the shard's first own sample; later shards have URH_COSTAS_HALO samples of the preceding shard stored in
+// front of it.  urh_costas_shard_speculate is asynchronous; urh_costas_shard_resolve needs the preceding shard's final
+// loop state (state_in = {freq, phase}; ignored on the first shard) and returns this shard's.
+static CsRun g_shard_run;  // one sharded PSK demodulation in flight per process (one process per GPU)
+
+extern "C" int urh_costas_halo_samples(void) { return CS_WARM; }
+
+extern "C" int urh_costas_shard_speculate(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int first_shard, float noise_mag,
+                                          int loop_order, float bandwidth, float* d_out) {
+    const int order = loop_order > 4 ? 4 : loop_order;
+    if (order != 2 && order != 4) URH_FAIL(ctx, URH_ERR_INVALID, "sharded PSK: loop order 2 or 4");
+    volatile float nm = noise_mag;
+    volatile float sq = nm * nm;
+    CsRun& R = g_shard_run;
+    URH_CHECK(cs_params(ctx, &R.P, dtype, sq, order, bandwidth));
+    R.iq = d_iq; R.dtype = dtype; R.n = n; R.first_shard = first_shard ? 1 : 0; R.out = d_out;
+    return cs_speculate(ctx, R);
+}
+
+extern "C" int urh_costas_shard_resolve(urh_ctx* ctx, const float* h_state_in, float* h_state_out) {
+    CsState in;
+    in.freq = h_state_in ? h_state_in[0] : 0.f;
+    in.phase = h_state_in ? h_state_in[1] : 1.5f;
+    return cs_resolve(ctx, g_shard_run, in, h_state_out);
 }
 
 // diagnostics of the last speculative run: {chunks resolved in O(1), chunks walked, samples stepped serially}

@@ -95,25 +95,52 @@ class ShardBuffer(object):
     """Device buffer [pad][halo][shard samples...]: the shard starts 256-byte aligned (full-line warp loads), the halo
     sample sits right before it."""
 
-    def __init__(self, ctx, n_local, dtype=np.float32):
+    def __init__(self, ctx, n_local, dtype=np.float32, halo=1):
         self.ctx = ctx
         self.n = int(n_local)
         self.dtype = np.dtype(dtype)
-        self.pad = 256 // (2 * self.dtype.itemsize)  # samples before the shard (>= 1 halo, keeps 256 B alignment)
+        self.halo_len = int(halo)
+        unit = 256 // (2 * self.dtype.itemsize)  # samples per 256 bytes
+        self.pad = ((self.halo_len + unit - 1) // unit) * unit  # samples before the shard (keeps 256 B alignment)
         self.buf = DeviceArray(ctx, (self.n + self.pad, 2), self.dtype)
         self.shard = self.buf[self.pad:]
-        self.halo = self.buf[self.pad - 1: self.pad]
+        self.halo = self.buf[self.pad - self.halo_len: self.pad]
 
 
 def exchange_halo(ctx, hx, sb: ShardBuffer):
-    """rank r receives the last sample of rank r-1's shard (NCCL all-gather of one sample per rank)"""
-    one = sb.shard[sb.n - 1: sb.n]
-    allv = DeviceArray(ctx, (hx.world, 2), sb.dtype)
-    ctx.check(ctx.lib.urh_nccl_allgather(ctx.handle, C.c_void_p(one.ptr), C.c_void_p(allv.ptr), one.nbytes))
+    """rank r receives the last `halo_len` samples of rank r-1's shard (NCCL all-gather of the tails)"""
+    h = sb.halo_len
+    assert sb.n >= h, "shard shorter than the halo"
+    tail = sb.shard[sb.n - h: sb.n]
+    allv = DeviceArray(ctx, (hx.world * h, 2), sb.dtype)
+    ctx.check(ctx.lib.urh_nccl_allgather(ctx.handle, C.c_void_p(tail.ptr), C.c_void_p(allv.ptr), tail.nbytes))
     if hx.rank > 0:
-        src = allv[hx.rank - 1: hx.rank]
+        src = allv[(hx.rank - 1) * h: hx.rank * h]
         ctx.check(ctx.lib.urh_memcpy_d2d(ctx.handle, C.c_void_p(sb.halo.ptr), C.c_void_p(src.ptr), src.nbytes))
     ctx.sync()
+
+
+def costas_halo(ctx) -> int:
+    return int(ctx.lib.urh_costas_halo_samples())
+
+
+def afp_demod_psk_sharded(ctx, rank, world, sb: ShardBuffer, noise_mag, mod_order, costas_loop_bandwidth, d_out):
+    """PSK demodulation (Costas loop) of a capture sharded over the ranks, bit-identical to the serial loop.  Every
+    rank speculates over its shard concurrently (the expensive pass); the loop state is then handed from rank to rank
+    (one 8-byte NCCL all-gather per rank) for the cheap chain-resolution pass.  sb needs a halo of costas_halo() samples."""
+    lib = ctx.lib
+    assert rank == 0 or sb.halo_len >= costas_halo(ctx)
+    ctx.check(lib.urh_costas_shard_speculate(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, int(rank == 0),
+                                             float(noise_mag), int(mod_order), float(costas_loop_bandwidth), C.c_void_p(d_out.ptr)))
+    state = np.zeros(2, dtype=np.float32)
+    for turn in range(world):
+        mine = np.zeros(2, dtype=np.float32)
+        if turn == rank:
+            ctx.check(lib.urh_costas_shard_resolve(ctx.handle, state.ctypes.data_as(C.c_void_p), mine.ctypes.data_as(C.c_void_p)))
+        every = np.empty((world, 2), dtype=np.float32)
+        ctx.check(lib.urh_nccl_allgather_host(ctx.handle, mine.ctypes.data_as(C.c_void_p), every.ctypes.data_as(C.c_void_p), mine.nbytes))
+        state = every[turn].copy()  # the loop state at the end of shard `turn`
+    return state
 
 
 def demod_digitize_sharded(ctx, hx, sb: ShardBuffer, global_offset, n_total, noise_mag, mod_type, center, tolerance,
