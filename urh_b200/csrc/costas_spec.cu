@@ -20,15 +20,16 @@
 
 #include <math.h>
 
-#define CS_CHUNK 4096
 #define CS_SEG 256
-#define CS_SEGS (CS_CHUNK / CS_SEG)
+#define CS_MAX_SEGS 16          // chunk = segs * 256 samples, segs in {2,4,8,16} chosen from the capture length
 #define CS_WARM 1024
 #define CS_MAXBR 4
 
 struct CsParams {
     float noise_sqrd, alpha, beta, scale, shift;
     int order;  // 2 or 4
+    int segs;   // segments per chunk
+    int chunk;  // samples per chunk = segs * CS_SEG
 };
 
 struct __align__(8) CsState {
@@ -79,6 +80,37 @@ __device__ __forceinline__ bool cs_step(CsState& s, float re, float im, const Cs
     return true;
 }
 
+// run the loop over samples [a, b): loads are issued four samples ahead of the dependent recurrence
+template <int DT, bool WRITE>
+__device__ __forceinline__ int cs_run(const void* iq, int64_t a, int64_t b, CsState& s, const CsParams& P, float* out, int) {
+    int cnt = 0;
+    float re[4], im[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        re[t] = im[t] = 0.f;
+        if (a + t < b) cs_load<DT>(iq, a + t, re[t], im[t]);
+    }
+    for (int64_t i0 = a; i0 < b; i0 += 4) {
+        float nre[4], nim[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            nre[t] = nim[t] = 0.f;
+            if (i0 + 4 + t < b) cs_load<DT>(iq, i0 + 4 + t, nre[t], nim[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            if (i0 + t < b) {
+                float o;
+                cnt += cs_step(s, re[t], im[t], P, o) ? 1 : 0;
+                if (WRITE) out[i0 + t] = o;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) { re[t] = nre[t]; im[t] = nim[t]; }
+    }
+    return cnt;
+}
+
 // pass 1: grid.x covers chunks, grid.y = candidate k
 template <int DT>
 __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ iq, int64_t n, CsParams P, int64_t nchunks,
@@ -87,9 +119,9 @@ __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ i
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (c >= nchunks) return;
-    const int64_t p0 = c * CS_CHUNK;
+    const int64_t p0 = c * P.chunk;
     float* out = cand + (int64_t)k * n;
-    CsState* ck = ckpt + ((int64_t)k * nchunks + c) * (CS_SEGS + 1);
+    CsState* ck = ckpt + ((int64_t)k * nchunks + c) * (P.segs + 1);
     CsState s;
     s.freq = 0.0f;
     // candidate k: the loop's initial phase 1.5 rotated by k * 2*pi/order (branch of the lock point)
@@ -103,25 +135,17 @@ __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ i
         // later shards of a sharded capture have CS_WARM halo samples stored in front of iq (negative indices)
         int64_t w0 = p0 - CS_WARM;
         if (first_shard && w0 < 1) w0 = 1;
-        for (int64_t i = w0; i < p0; i++) {
-            float re, im;
-            cs_load<DT>(iq, i, re, im);
-            cs_step(s, re, im, P, o);
-        }
+        cs_run<DT, false>(iq, w0, p0, s, P, nullptr, 0);
     }
     ck[0] = s;
-    for (int j = 0; j < CS_SEGS; j++) {
+    for (int j = 0; j < P.segs; j++) {
         const int64_t a = p0 + (int64_t)j * CS_SEG;
-        int cnt = 0;
-        for (int64_t i = a; i < a + CS_SEG && i < n; i++) {
-            if (i == 0 && first_shard) { out[0] = 0.0f; continue; }  // the reference loop starts at i = 1 (result[0] undefined -> 0)
-            float re, im;
-            cs_load<DT>(iq, i, re, im);
-            cnt += cs_step(s, re, im, P, o) ? 1 : 0;
-            out[i] = o;
-        }
+        int64_t a0 = a;
+        if (a0 == 0 && first_shard) { out[0] = 0.0f; a0 = 1; }  // the reference loop starts at i = 1 (result[0] undefined -> 0)
+        const int64_t b0 = min(a + (int64_t)CS_SEG, n);
+        const int cnt = cs_run<DT, true>(iq, a0, b0, s, P, out, 0);
         ck[j + 1] = s;
-        if (k == 0) nonnoise[c * CS_SEGS + j] = cnt;
+        if (k == 0) nonnoise[c * P.segs + j] = cnt;
     }
 }
 
@@ -136,8 +160,8 @@ __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, 
     const int lane = threadIdx.x;
     // first shard: true state at the end of chunk 0 (exact run); later shards: the state handed over by the
     // preceding shard, and chunk 0 is resolved like every other chunk
-    CsState st = first_shard ? ckpt[CS_SEGS] : st_in;
-    if (first_shard && lane < CS_SEGS) src[lane] = 0;
+    CsState st = first_shard ? ckpt[P.segs] : st_in;
+    if (first_shard && lane < P.segs) src[lane] = 0;
     int64_t fast = 0, slow = 0, stepped = 0;
     for (int64_t c0 = first_shard ? 1 : 0; c0 < nchunks; c0 += 32) {
         // every lane prefetches the candidates' start/end states of chunk c0 + lane
@@ -146,9 +170,9 @@ __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, 
 #pragma unroll
         for (int k = 0; k < CS_MAXBR; k++) {
             if (k < nbr && cl < nchunks) {
-                const CsState* ck = ckpt + ((int64_t)k * nchunks + cl) * (CS_SEGS + 1);
+                const CsState* ck = ckpt + ((int64_t)k * nchunks + cl) * (P.segs + 1);
                 s0[k] = ck[0];
-                s1[k] = ck[CS_SEGS];
+                s1[k] = ck[P.segs];
             } else {
                 s0[k].freq = s0[k].phase = s1[k].freq = s1[k].phase = __int_as_float(0x7fc00000);
             }
@@ -171,37 +195,54 @@ __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, 
                 }
             }
             if (match >= 0) {  // O(1): the candidate's run is the true run
-                if (lane < CS_SEGS) src[c * CS_SEGS + lane] = (uint8_t)match;
+                if (lane < P.segs) src[c * P.segs + lane] = (uint8_t)match;
                 st = e;
                 fast++;
                 continue;
             }
             slow++;
             // walk the chunk from the true state; lane 0 computes, the decision is broadcast
-            int merged = -1, jm = CS_SEGS;
-            for (int j = 0; j < CS_SEGS; j++) {
-                const int cnt = nonnoise[c * CS_SEGS + j];
+            int merged = -1, jm = P.segs;
+            for (int j = 0; j < P.segs; j++) {
+                const int cnt = nonnoise[c * P.segs + j];
                 if (cnt == 0) {  // state frozen, every candidate holds NOISE here
-                    if (lane == 0) src[c * CS_SEGS + j] = 0;
+                    if (lane == 0) src[c * P.segs + j] = 0;
                     continue;
                 }
-                const int64_t a = c * CS_CHUNK + (int64_t)j * CS_SEG;
-                if (lane == 0) {
-                    for (int64_t i = a; i < a + CS_SEG && i < n; i++) {
-                        float re, im, o;
+                const int64_t a = c * P.chunk + (int64_t)j * CS_SEG;
+                // the warp stages the segment (coalesced) and evaluates the noise gate in parallel; lane 0 then
+                // advances the loop over the non-noise samples only
+                for (int g = 0; g < CS_SEG / 32; g++) {
+                    const int64_t i = a + g * 32 + lane;
+                    float re = 0.f, im = 0.f;
+                    bool live = false;
+                    if (i < n && !(i == 0 && first_shard)) {
                         cs_load<DT>(iq, i, re, im);
-                        cs_step(st, re, im, P, o);
-                        out[i] = o;
+                        live = !(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)) <= P.noise_sqrd);
+                        if (!live) out[i] = -4.0f;
+                    } else if (i == 0 && first_shard) {
+                        out[0] = 0.0f;
                     }
-                    src[c * CS_SEGS + j] = 255;
+                    unsigned mask = __ballot_sync(URH_FULL_MASK, live);
+                    while (mask) {
+                        const int l = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float r1 = __shfl_sync(URH_FULL_MASK, re, l), i1 = __shfl_sync(URH_FULL_MASK, im, l);
+                        if (lane == 0) {
+                            float o;
+                            cs_step(st, r1, i1, P, o);
+                            out[a + g * 32 + l] = o;
+                        }
+                    }
                 }
-                stepped += CS_SEG;
+                if (lane == 0) src[c * P.segs + j] = 255;
+                stepped += cnt;
                 st.freq = __shfl_sync(URH_FULL_MASK, st.freq, 0);
                 st.phase = __shfl_sync(URH_FULL_MASK, st.phase, 0);
                 // does the true state now coincide with a candidate checkpoint?
                 int m = -1;
                 if (lane < nbr) {
-                    const CsState q = ckpt[((int64_t)lane * nchunks + c) * (CS_SEGS + 1) + j + 1];
+                    const CsState q = ckpt[((int64_t)lane * nchunks + c) * (P.segs + 1) + j + 1];
                     if (__float_as_uint(q.freq) == __float_as_uint(st.freq) && __float_as_uint(q.phase) == __float_as_uint(st.phase)) m = lane;
                 }
                 const unsigned any = __ballot_sync(URH_FULL_MASK, m >= 0);
@@ -212,8 +253,8 @@ __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, 
                 }
             }
             if (merged >= 0) {
-                if (lane >= jm && lane < CS_SEGS) src[c * CS_SEGS + lane] = (uint8_t)merged;
-                const CsState q = ckpt[((int64_t)merged * nchunks + c) * (CS_SEGS + 1) + CS_SEGS];
+                if (lane >= jm && lane < P.segs) src[c * P.segs + lane] = (uint8_t)merged;
+                const CsState q = ckpt[((int64_t)merged * nchunks + c) * (P.segs + 1) + P.segs];
                 st = q;
             }
         }
@@ -247,6 +288,8 @@ static int cs_params(urh_ctx* ctx, CsParams* P, int dtype, float noise_sqrd, int
     P->beta = (float)(((4.0 * bw) * bw) / den);
     P->noise_sqrd = noise_sqrd;
     P->order = order;
+    P->segs = 16;
+    P->chunk = P->segs * CS_SEG;
     switch (dtype) {
         case URH_DT_I8: P->scale = 127.5f; P->shift = 0.5f; break;
         case URH_DT_U8: P->scale = 127.5f; P->shift = -127.5f; break;
@@ -274,12 +317,17 @@ struct CsRun {
 
 static int cs_speculate(urh_ctx* ctx, CsRun& R) {
     urh_arena_reset(ctx);
-    R.nchunks = urh_div_up(R.n, CS_CHUNK);
+    // enough independent chains to fill the GPU: shrink the chunk for short captures (more warm-up overhead)
+    int segs = 16;
+    while (segs > 2 && (R.n / (segs * CS_SEG)) * R.P.order < (int64_t)ctx->sm_count * 1024) segs >>= 1;
+    R.P.segs = segs;
+    R.P.chunk = segs * CS_SEG;
+    R.nchunks = urh_div_up(R.n, R.P.chunk);
     R.nbr = R.P.order;  // candidates = lock branches
     URH_CHECK(urh_arena(ctx, (size_t)R.nbr * R.n, &R.cand));
-    URH_CHECK(urh_arena(ctx, (size_t)R.nbr * R.nchunks * (CS_SEGS + 1), &R.ckpt));
-    URH_CHECK(urh_arena(ctx, (size_t)R.nchunks * CS_SEGS, &R.nonnoise));
-    URH_CHECK(urh_arena(ctx, (size_t)R.nchunks * CS_SEGS, &R.src));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nbr * R.nchunks * (R.P.segs + 1), &R.ckpt));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nchunks * R.P.segs, &R.nonnoise));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nchunks * R.P.segs, &R.src));
     URH_CHECK(urh_arena(ctx, 4, &R.stats));
     URH_CHECK(urh_arena(ctx, 2, &R.st_out));
     const dim3 grid((unsigned)urh_div_up(R.nchunks, 128), (unsigned)R.nbr);
@@ -314,7 +362,7 @@ static int cs_resolve(urh_ctx* ctx, CsRun& R, CsState st_in, float* h_state_out)
 int urh_costas_demod(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_sqrd, int loop_order, float bandwidth,
                      float* d_out) {
     const int order = loop_order > 4 ? 4 : loop_order;  // pyx:285-287
-    if (n < 4 * CS_CHUNK || (order != 2 && order != 4))
+    if (n < 4 * 512 * 4 || (order != 2 && order != 4))
         return urh_costas_demod_serial(ctx, d_iq, dtype, n, noise_sqrd, loop_order, bandwidth, d_out);
     CsRun R;
     URH_CHECK(cs_params(ctx, &R.P, dtype, noise_sqrd, order, bandwidth));

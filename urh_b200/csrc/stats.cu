@@ -182,13 +182,21 @@ template <int PASS>
 __global__ void __launch_bounds__(256) k_center_pass(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ prefix,
                                                     int64_t r0, int64_t r1, double mean, double hmin, double hstep,
                                                     int64_t nbins, CenStats* __restrict__ partial,
-                                                    unsigned long long* __restrict__ hist) {
-    const int64_t base = (int64_t)blockIdx.x * CEN_TILE;
-    const int64_t tile_rank0 = prefix[blockIdx.x];
-    const int64_t tile_cnt = prefix[blockIdx.x + 1] - tile_rank0;
-    double sum = 0.0;
+                                                    unsigned long long* __restrict__ hist, int64_t ntiles, int hist_in_smem) {
+    double sum = 0.0, sumsq = 0.0;
     float mn = INFINITY, mx = -INFINITY;
     long long cnt = 0;
+    // PASS 2: block-private histogram in shared memory when the bins fit (flushed once per block)
+    extern __shared__ unsigned int s_hist[];
+    const bool smem_hist = (PASS == 2) && hist_in_smem;
+    if (smem_hist) {
+        for (int64_t b = threadIdx.x; b < nbins; b += 256) s_hist[b] = 0u;
+        __syncthreads();
+    }
+    for (int64_t tile_idx = blockIdx.x; tile_idx < ntiles; tile_idx += gridDim.x) {
+    const int64_t base = tile_idx * CEN_TILE;
+    const int64_t tile_rank0 = prefix[tile_idx];
+    const int64_t tile_cnt = prefix[tile_idx + 1] - tile_rank0;
     if (tile_cnt > 0 && tile_rank0 < r1 && tile_rank0 + tile_cnt > r0) {
         // thread t owns elements [t*16, t*16+16) of the tile (blocked, so ranks are monotone in t)
         const int per = CEN_TILE / 256;
@@ -217,6 +225,7 @@ __global__ void __launch_bounds__(256) k_center_pass(const float* __restrict__ x
                 if (rank >= r0 && rank < r1) {
                     if (PASS == 0) {
                         sum += (double)v[j];
+                        sumsq += (double)v[j] * (double)v[j];
                         mn = fminf(mn, v[j]);
                         mx = fmaxf(mx, v[j]);
                         cnt++;
@@ -233,23 +242,35 @@ __global__ void __launch_bounds__(256) k_center_pass(const float* __restrict__ x
                         while (k > 0 && a < hmin + (double)k * hstep) k--;
                         while (k < nbins - 1 && a >= hmin + (double)(k + 1) * hstep) k++;
                         const double last_edge = hmin + (double)nbins * hstep;
-                        if (a >= hmin && a <= last_edge) atomicAdd(&hist[k], 1ull);
+                        if (a >= hmin && a <= last_edge) {
+                            if (smem_hist) atomicAdd(&s_hist[k], 1u);
+                            else atomicAdd(&hist[k], 1ull);
+                        }
                     }
                 }
                 rank++;
             }
         }
+        __syncthreads();  // s_pre is reused by the next tile
+    }
+    }
+    if (smem_hist) {
+        __syncthreads();
+        for (int64_t b = threadIdx.x; b < nbins; b += 256)
+            if (s_hist[b]) atomicAdd(&hist[b], (unsigned long long)s_hist[b]);
     }
     if (PASS < 2) {
         __shared__ double s_sum[256];
+        __shared__ double s_sq[256];
         __shared__ float s_mn[256], s_mx[256];
         __shared__ long long s_cnt[256];
         __syncthreads();
-        s_sum[threadIdx.x] = sum; s_mn[threadIdx.x] = mn; s_mx[threadIdx.x] = mx; s_cnt[threadIdx.x] = cnt;
+        s_sum[threadIdx.x] = sum; s_sq[threadIdx.x] = sumsq; s_mn[threadIdx.x] = mn; s_mx[threadIdx.x] = mx; s_cnt[threadIdx.x] = cnt;
         __syncthreads();
         for (int off = 128; off > 0; off >>= 1) {
             if (threadIdx.x < off) {
                 s_sum[threadIdx.x] += s_sum[threadIdx.x + off];
+                s_sq[threadIdx.x] += s_sq[threadIdx.x + off];
                 s_mn[threadIdx.x] = fminf(s_mn[threadIdx.x], s_mn[threadIdx.x + off]);
                 s_mx[threadIdx.x] = fmaxf(s_mx[threadIdx.x], s_mx[threadIdx.x + off]);
                 s_cnt[threadIdx.x] += s_cnt[threadIdx.x + off];
@@ -258,28 +279,30 @@ __global__ void __launch_bounds__(256) k_center_pass(const float* __restrict__ x
         }
         if (threadIdx.x == 0) {
             CenStats o;
-            o.sum = s_sum[0]; o.sumsq = 0.0; o.mn = s_mn[0]; o.mx = s_mx[0]; o.cnt = s_cnt[0];
+            o.sum = s_sum[0]; o.sumsq = s_sq[0]; o.mn = s_mn[0]; o.mx = s_mx[0]; o.cnt = s_cnt[0];
             partial[blockIdx.x] = o;
         }
     }
 }
 
 __global__ void __launch_bounds__(256) k_center_fold(const CenStats* __restrict__ partial, int64_t ntiles, CenStats* __restrict__ out) {
-    double sum = 0.0;
+    double sum = 0.0, sq = 0.0;
     float mn = INFINITY, mx = -INFINITY;
     long long cnt = 0;
     for (int64_t t = threadIdx.x; t < ntiles; t += 256) {
         const CenStats p = partial[t];
-        sum += p.sum; mn = fminf(mn, p.mn); mx = fmaxf(mx, p.mx); cnt += p.cnt;
+        sum += p.sum; sq += p.sumsq; mn = fminf(mn, p.mn); mx = fmaxf(mx, p.mx); cnt += p.cnt;
     }
     __shared__ double s_sum[256];
+    __shared__ double s_sq[256];
     __shared__ float s_mn[256], s_mx[256];
     __shared__ long long s_cnt[256];
-    s_sum[threadIdx.x] = sum; s_mn[threadIdx.x] = mn; s_mx[threadIdx.x] = mx; s_cnt[threadIdx.x] = cnt;
+    s_sum[threadIdx.x] = sum; s_sq[threadIdx.x] = sq; s_mn[threadIdx.x] = mn; s_mx[threadIdx.x] = mx; s_cnt[threadIdx.x] = cnt;
     __syncthreads();
     for (int off = 128; off > 0; off >>= 1) {
         if (threadIdx.x < off) {
             s_sum[threadIdx.x] += s_sum[threadIdx.x + off];
+            s_sq[threadIdx.x] += s_sq[threadIdx.x + off];
             s_mn[threadIdx.x] = fminf(s_mn[threadIdx.x], s_mn[threadIdx.x + off]);
             s_mx[threadIdx.x] = fmaxf(s_mx[threadIdx.x], s_mx[threadIdx.x + off]);
             s_cnt[threadIdx.x] += s_cnt[threadIdx.x + off];
@@ -288,7 +311,7 @@ __global__ void __launch_bounds__(256) k_center_fold(const CenStats* __restrict_
     }
     if (threadIdx.x == 0) {
         CenStats o;
-        o.sum = s_sum[0]; o.sumsq = 0.0; o.mn = s_mn[0]; o.mx = s_mx[0]; o.cnt = s_cnt[0];
+        o.sum = s_sum[0]; o.sumsq = s_sq[0]; o.mn = s_mn[0]; o.mx = s_mx[0]; o.cnt = s_cnt[0];
         *out = o;
     }
 }
@@ -306,7 +329,7 @@ extern "C" int urh_center_stats(urh_ctx* ctx, const float* d_x, int64_t n, int64
     CenStats* folded;
     URH_CHECK(urh_arena(ctx, (size_t)ntiles + 1, &prefix));
     URH_CHECK(urh_arena(ctx, 4, &d_total));
-    URH_CHECK(urh_arena(ctx, (size_t)ntiles, &partial));
+    URH_CHECK(urh_arena(ctx, (size_t)ctx->sm_count * 8 + 8, &partial));
     URH_CHECK(urh_arena(ctx, 2, &folded));
     URH_LAUNCH(ctx, k_count_valid, (unsigned)ntiles, 256, 0, d_x, n, prefix);
     URH_CHECK((urhscan::device_scan<int64_t, urhscan::AddI64>(ctx, prefix, ntiles, urhscan::AddI64(), (int64_t)0, true, d_total)));
@@ -318,19 +341,18 @@ extern "C" int urh_center_stats(urh_ctx* ctx, const float* d_x, int64_t n, int64
     if (max_size >= 0 && r1 - r0 > max_size) r1 = r0 + max_size;
     h_out[0] = (double)total; h_out[1] = (double)r0; h_out[2] = (double)r1;
     if (r1 <= r0) return URH_OK;
-    URH_LAUNCH(ctx, (k_center_pass<0>), (unsigned)ntiles, 256, 0, d_x, n, prefix, r0, r1, 0.0, 0.0, 1.0, (int64_t)0, partial, nullptr);
-    URH_LAUNCH(ctx, k_center_fold, 1, 256, 0, partial, ntiles, folded);
+    const unsigned gs = (unsigned)min(ntiles, (int64_t)ctx->sm_count * 8);
+    URH_LAUNCH(ctx, (k_center_pass<0>), gs, 256, 0, d_x, n, prefix, r0, r1, 0.0, 0.0, 1.0, (int64_t)0, partial, nullptr, ntiles, 0);
+    URH_LAUNCH(ctx, k_center_fold, 1, 256, 0, partial, (int64_t)gs, folded);
     CenStats st;
     URH_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, folded, sizeof(CenStats), cudaMemcpyDeviceToHost, ctx->stream));
     URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(&st, ctx->h_mail, sizeof(st));
     const double mean = st.sum / (double)st.cnt;
-    URH_LAUNCH(ctx, (k_center_pass<1>), (unsigned)ntiles, 256, 0, d_x, n, prefix, r0, r1, mean, 0.0, 1.0, (int64_t)0, partial, nullptr);
-    URH_LAUNCH(ctx, k_center_fold, 1, 256, 0, partial, ntiles, folded);
+    // population variance from the double sums (np.var semantics; the reference's float32 pairwise result differs ~1e-7)
     CenStats sv;
-    URH_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, folded, sizeof(CenStats), cudaMemcpyDeviceToHost, ctx->stream));
-    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(&sv, ctx->h_mail, sizeof(sv));
+    sv.sum = st.sumsq - (double)st.cnt * mean * mean;
+    if (sv.sum < 0.0) sv.sum = 0.0;
     h_out[3] = (double)st.mn; h_out[4] = (double)st.mx; h_out[5] = mean; h_out[6] = sv.sum / (double)st.cnt;
     return URH_OK;
 }
@@ -351,7 +373,10 @@ extern "C" int urh_center_histogram(urh_ctx* ctx, const float* d_x, int64_t n, i
     URH_CHECK((urhscan::device_scan<int64_t, urhscan::AddI64>(ctx, prefix, ntiles, urhscan::AddI64(), (int64_t)0, true, d_total)));
     URH_CUDA(ctx, cudaMemcpyAsync(prefix + ntiles, d_total, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
     URH_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(unsigned long long), ctx->stream));
-    URH_LAUNCH(ctx, (k_center_pass<2>), (unsigned)ntiles, 256, 0, d_x, n, prefix, r0, r1, 0.0, hmin, hstep, nbins, nullptr, hist);
+    const int in_smem = nbins <= 12000 ? 1 : 0;
+    const unsigned gs = (unsigned)min(ntiles, (int64_t)ctx->sm_count * 8);
+    URH_LAUNCH(ctx, (k_center_pass<2>), gs, 256, in_smem ? (size_t)nbins * sizeof(unsigned int) : 0, d_x, n, prefix, r0, r1, 0.0, hmin,
+               hstep, nbins, nullptr, hist, ntiles, in_smem);
     URH_CUDA(ctx, cudaMemcpyAsync(h_hist, hist, (size_t)nbins * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return URH_OK;
