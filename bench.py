@@ -103,7 +103,7 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_arm(n_cpu, steps, warmup, iq_slice=None):
+def cpu_reference_arm(n_cpu, steps, warmup, iq_slice=None, detect=True):
     """Time the reference's own CPU implementation (oracle/_ref compiled from /root/reference if it travelled
     here, else the C oracle port) of afp_demod(FSK) + grab_pulse_lens on a bounded slice, all host threads."""
     from oracle import oracle, ref_loader
@@ -131,14 +131,17 @@ def cpu_reference_arm(n_cpu, steps, warmup, iq_slice=None):
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         q = demod(iq_slice, NOISE_MAG, "FSK", 2)
-        rows = grab(q, CENTER, TOL, "FSK", SPS)
+        # detect_center is numpy code in the reference (AutoInterpretation.py:226-290); oracle.detect_center restates it
+        center = oracle.detect_center(q) if detect else CENTER
+        rows = grab(q, center, TOL, "FSK", SPS)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     sec = float(np.mean(times))
     return {"value": n_cpu / sec / 1e6, "unit": "MSamples/s", "cores": cores, "kind": kind,
-            "sample": "%d-sample slice of the same synthetic 2-FSK capture (afp_demod FSK + grab_pulse_lens), mean of %d"
-                      % (n_cpu, len(times)), "ms_per_step": sec * 1e3, "rows": int(len(rows))}
+            "sample": "%d-sample slice of the same synthetic 2-FSK capture (afp_demod FSK%s + grab_pulse_lens), mean of %d"
+                      % (n_cpu, " + detect_center (numpy, as in the reference)" if detect else "", len(times)),
+            "ms_per_step": sec * 1e3, "rows": int(len(rows))}
 
 
 def host_synth(n, seed=0):
@@ -165,6 +168,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=30, help="samples per GPU = 2**log2n (default 1 GiSample)")
     ap.add_argument("--cpu-log2n", type=int, default=24)
+    ap.add_argument("--center", default="detect", choices=["detect", "given"],
+                    help="detect: demod + detect_center + digitize (BASELINE configs[1]); given: fused demod+digitize, center known")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -174,7 +179,9 @@ def main():
     world = env_int("WORLD_SIZE", 1)
     n = 1 << args.log2n
     workload = ("2-FSK complex64, ONE capture of %d x 2^%d samples sharded by contiguous range (1-sample halo, NCCL run stitching) "
-                "@2MS/s sps=100 +-20kHz AWGN sigma=0.01 bursts+gaps; demod+digitize (center=0, tol=5, noise=0.05)" % (world, args.log2n))
+                "@2MS/s sps=100 +-20kHz AWGN sigma=0.01 bursts+gaps; %s (tol=5, noise=0.05)"
+                % (world, args.log2n, "demod + detect_center (capture-wide) + digitize" if args.center == "detect"
+                   else "fused demod+digitize, center=0 given"))
     base = {"metric": "MSamples/s IQ demod+digitize (complex64)", "unit": "MSamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -183,7 +190,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = cpu_reference_arm(1 << args.cpu_log2n, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+        r = cpu_reference_arm(1 << args.cpu_log2n, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)), detect=args.center == "detect")
         line = dict(base)
         line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"],
                      "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -230,14 +237,44 @@ def main():
         udist.init_nccl(ctx, hx)
         udist.exchange_halo(ctx, hx, sb)
 
-    def step_resident():
+    from urh_b200.ainterpretation import AutoInterpretation as AI
+
+    dense_of_step = [0.0]
+
+    def read_dense_ms():
+        ms = C.c_float()
+        lib.urh_last_dense_ms(ctx.handle, C.byref(ms))
+        return ms.value
+
+    def step_given():
         if world > 1:
-            return udist.demod_digitize_distributed(ctx, rank, world, sb, offset, n_total, NOISE_MAG, "FSK", CENTER, TOL, SPS,
-                                                    d_qad=d_qad, fetch=False)
+            k = udist.demod_digitize_distributed(ctx, rank, world, sb, offset, n_total, NOISE_MAG, "FSK", CENTER, TOL, SPS,
+                                                 d_qad=d_qad, fetch=False)
+            dense_of_step[0] = read_dense_ms()
+            return k
         k = C.c_int64(0)
         ctx.check(lib.urh_demod_digitize(ctx.handle, C.c_void_p(d_iq.ptr), _lib.DT_F32, n, NOISE_MAG, _lib.MOD_FSK,
                                          CENTER, TOL, SPS, 1, 0.1, C.c_void_p(d_qad.ptr), C.byref(k)))
+        dense_of_step[0] = read_dense_ms()
         return k.value
+
+    center_seen = [None]
+
+    def step_detect():
+        if world > 1:
+            center = udist.detect_center_distributed(ctx, rank, world, sb, NOISE_MAG, "FSK", d_qad)
+            dense_of_step[0] = read_dense_ms()
+            center_seen[0] = center
+            return udist.demod_digitize_distributed(ctx, rank, world, sb, offset, n_total, NOISE_MAG, "FSK", float(center), TOL, SPS,
+                                                    fetch=False)
+        _, center = AI.demod_detect_center(d_iq, NOISE_MAG, "FSK", out=d_qad)
+        dense_of_step[0] = read_dense_ms()
+        center_seen[0] = center
+        k = C.c_int64(0)
+        ctx.check(lib.urh_grab_pulse_lens(ctx.handle, C.c_void_p(d_qad.ptr), n, float(center), TOL, _lib.MOD_FSK, SPS, 1, 0.1, C.byref(k)))
+        return k.value
+
+    step_resident = step_detect if args.center == "detect" else step_given
 
     def barrier():
         ctx.sync()
@@ -257,9 +294,7 @@ def main():
     ctx.timer_start()
     for _ in range(args.steps):
         k_rows = step_resident()
-        ms = C.c_float()
-        lib.urh_last_dense_ms(ctx.handle, C.byref(ms))
-        dense_ms.append(ms.value)
+        dense_ms.append(dense_of_step[0])
     total_ms = ctx.timer_stop()
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -272,6 +307,58 @@ def main():
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # ---- the other variant, for the record (not the headline): same capture, same timing rules, fewer steps ------
+    other = step_given if args.center == "detect" else step_detect
+    other_steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        other()
+    barrier()
+    other_dense = []
+    ctx.timer_start()
+    for _ in range(other_steps):
+        other()
+        other_dense.append(dense_of_step[0])
+    other_ms = ctx.timer_stop()
+    barrier()
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([other_ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        other_ms = float(t.item())
+    other_ms /= other_steps
+    other_line = {"variant": "fused demod+digitize, center=0 given" if args.center == "detect" else "demod + detect_center + digitize",
+                  "value": world * n / (other_ms * 1e-3) / 1e6, "unit": "MSamples/s", "ms_per_step": other_ms, "steps": other_steps,
+                  "dense_kernel_ms": float(np.mean(other_dense))}
+
+    # stage breakdown of the detect variant at N=1 (device timers around each public call; diagnostic)
+    stages = None
+    if world == 1:
+        stages = {}
+        kept = C.c_int64(0)
+        w5 = np.zeros(5)
+        reps = 3
+        acc = {"demod+tile_stats": 0.0, "window_stats": 0.0, "histogram+peaks": 0.0, "digitize(qad)": 0.0}
+        for _ in range(reps):
+            ctx.timer_start()
+            ctx.check(lib.urh_afp_demod_tiles(ctx.handle, C.c_void_p(d_iq.ptr), _lib.DT_F32, n, NOISE_MAG, _lib.MOD_FSK,
+                                              C.c_void_p(d_qad.ptr), 0, C.byref(kept)))
+            acc["demod+tile_stats"] += ctx.timer_stop()
+            r0, r1 = AI.center_rank_window(kept.value)
+            ctx.timer_start()
+            ctx.check(lib.urh_center_window_stats(ctx.handle, C.c_void_p(d_qad.ptr), n, r0, r1, w5.ctypes.data_as(C.c_void_p)))
+            acc["window_stats"] += ctx.timer_stop()
+            st = AI.center_stats_from_window(kept.value, r0, r1, w5)
+            t0 = time.perf_counter()
+            c = AI._center_from_stats(ctx, d_qad, n, st, lib.urh_center_histogram_tiles)
+            ctx.sync()
+            acc["histogram+peaks"] += (time.perf_counter() - t0) * 1e3
+            k = C.c_int64(0)
+            ctx.timer_start()
+            ctx.check(lib.urh_grab_pulse_lens(ctx.handle, C.c_void_p(d_qad.ptr), n, float(c), TOL, _lib.MOD_FSK, SPS, 1, 0.1, C.byref(k)))
+            acc["digitize(qad)"] += ctx.timer_stop()
+        stages = {k_: v / reps for k_, v in acc.items()}
 
     # ---- end-to-end through the public API with HOST buffers ----------------------------------------------
     e2e = None
@@ -286,12 +373,16 @@ def main():
             def step_e2e():
                 sb2.shard.set_async(host.array)
                 sb2.halo.set(halo)
+                if args.center == "detect":
+                    return udist.demod_center_digitize_distributed(ctx, rank, world, sb2, offset, n_total, NOISE_MAG, "FSK", TOL, SPS, d_qad)[1]
                 return udist.demod_digitize_distributed(ctx, rank, world, sb2, offset, n_total, NOISE_MAG, "FSK", CENTER, TOL, SPS)
         else:
             d_e2e = DeviceArray(ctx, (n, 2), np.float32)
 
             def step_e2e():
                 d_e2e.set_async(host.array)
+                if args.center == "detect":
+                    return sf.demod_center_digitize(d_e2e, NOISE_MAG, "FSK", TOL, SPS)[1]
                 qad, rows = sf.demod_digitize(d_e2e, NOISE_MAG, "FSK", CENTER, TOL, SPS, return_qad=False)
                 return rows
 
@@ -312,7 +403,8 @@ def main():
             e2e_ms = float(t.item())
         e2e = {"value": world * n / (e2e_ms / e2e_steps * 1e-3) / 1e6, "unit": "MSamples/s",
                "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(rows.nbytes), "steps": e2e_steps,
-               "api": "urh_b200.cythonext.signal_functions.demod_digitize(pinned host IQ) -> pulse table on host"}
+               "api": "urh_b200.cythonext.signal_functions.%s(pinned host IQ) -> pulse table on host"
+                      % ("demod_center_digitize" if args.center == "detect" else "demod_digitize")}
         assert len(rows) == k_rows
         # size-independent property of the digitizer: the pulse lengths of the whole capture sum to n_total - tolerance
         lens = int(rows[:, 1].sum())
@@ -338,7 +430,8 @@ def main():
     dense = float(np.mean(dense_ms))
     achieved = ALG_BYTES_PER_SAMPLE * n / (dense * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_dense_iq<F32,FSK,DIGITIZE>", "kernel_ms": dense,
+                "traffic": None, "kernel": "k_fsk_fast<F32,WRITE,STATS> (demod + tile statistics)" if args.center == "detect"
+                else "k_fsk_fast<F32,DIGITIZE,WRITE> (fused demod + classify + runs)", "kernel_ms": dense,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_SAMPLE * n, "peak_source": peak_src,
                 "kernel_share_of_step": dense / ms_per_step}
 
@@ -353,6 +446,7 @@ def main():
     line = dict(base)
     line.update({"value": value, "ms_per_step": ms_per_step, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                  "gpu_launches": int(launches), "clocks": clocks, "pulse_rows_per_step": int(k_rows),
+                 "detected_center": center_seen[0], "other_variant": other_line, "stage_ms": stages,
                  "device": info["name"], "sm_count": info["sm_count"]})
     print(json.dumps(line))
     return 0

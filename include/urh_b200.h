@@ -102,6 +102,17 @@ int urh_noise_chunk_stats(urh_ctx* ctx, const void* d_mags, int is_f64, int64_t 
 int urh_center_stats(urh_ctx* ctx, const float* d_x, int64_t n, int64_t max_size, double* h_out);
 int urh_center_histogram(urh_ctx* ctx, const float* d_x, int64_t n, int64_t r0, int64_t r1, double hmin, double hstep,
                          int64_t nbins, int64_t* h_hist);
+/* detect_center fused with demodulation (AutoInterpretation.py:183-240 after signal_functions.pyx:282 afp_demod):
+ * urh_afp_demod_tiles writes qad AND keeps, from the one pass over the IQ samples, per-tile {count, min, max, sum, sumsq}
+ * of the samples detect_center keeps; *h_kept = their number.  The caller forms the rank window [r0, r1) (5 %..95 %,
+ * capped by max_size; a shard subtracts its rank offset), urh_center_window_stats returns h_out5 = {count, min, max, sum,
+ * sumsq} inside it (a shard all-reduces these), and urh_center_histogram_tiles is then the only extra pass over qad.
+ * halo != 0: the previous shard's last sample is stored right before d_iq (as for urh_shard_dense). */
+int urh_afp_demod_tiles(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_mag, int mod_type, float* d_qad_out,
+                        int halo, int64_t* h_kept);
+int urh_center_window_stats(urh_ctx* ctx, const float* d_qad, int64_t n, int64_t r0, int64_t r1, double* h_out5);
+int urh_center_histogram_tiles(urh_ctx* ctx, const float* d_qad, int64_t n, int64_t r0, int64_t r1, double hmin, double hstep,
+                               int64_t nbins, int64_t* h_hist);
 /* replaces auto_interpretation.segment_messages_from_magnitudes (auto_interpretation.pyx:55-111) */
 int urh_segment_messages(urh_ctx* ctx, const void* d_mags, int is_f64, int64_t n, float noise_threshold,
                          int64_t* h_segments, int64_t cap, int64_t* k);

@@ -45,6 +45,10 @@ def main():
         part = udist.demod_digitize_distributed(ctx, rank, world, sb, lo, n, noise, mod, center, tol, sps)
         parts = hx.allgather(part)
         noise_sh = udist.detect_noise_level_sharded(ctx, hx, sb, lo, n)
+        d_qad2 = DeviceArray(ctx, (hi - lo,), np.float32)
+        c_sh, part_c = udist.demod_center_digitize_distributed(ctx, rank, world, sb, lo, n, noise, mod, tol, sps, d_qad2)
+        parts_c = hx.allgather(part_c)
+        centers = hx.allgather(c_sh)
         if rank == 0:
             qad_ref, rows_ref = sf.demod_digitize(iq, noise, mod, center, tol, sps)
             if not np.array_equal(np.concatenate(qads).view(np.uint32), qad_ref.view(np.uint32)):
@@ -55,6 +59,13 @@ def main():
                 failures.append(("rows_distributed", case))
             if noise_sh != AI.detect_noise_level_iq(iq):
                 failures.append(("noise", case, noise_sh))
+            c_one, rows_one = sf.demod_center_digitize(iq, noise, mod, tol, sps)
+            if any(c != centers[0] for c in centers):
+                failures.append(("center differs between ranks", case, centers))
+            if (c_one is None) != (c_sh is None) or (c_one is not None and abs(c_one - c_sh) > 1e-9 * max(1.0, abs(c_one))):
+                failures.append(("center", case, c_sh, c_one))
+            elif c_one is not None and not np.array_equal(udist.merge_shard_rows(parts_c), sf.grab_pulse_lens(qad_ref, c_sh, tol, mod, sps)):
+                failures.append(("rows_center", case))
     # PSK: speculative Costas loop over shards == single-GPU == oracle (bit-exact)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from test_gpu_costas import synth_psk

@@ -102,3 +102,49 @@ def test_estimate_matches_golden(AI):
             assert res["tolerance"] == est["tolerance"]
             assert res["noise"] == est["noise"]
             assert abs(res["center"] - est["center"]) <= 1e-5 * max(1.0, abs(est["center"]))
+
+
+# ---- demod + detect_center from one pass ------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CAPTURES)
+def test_demod_detect_center_matches_two_step_golden(AI, name):
+    """urh_afp_demod_stats + urh_center_histogram_tiles == afp_demod followed by detect_center (golden from the reference)."""
+    g = load_golden("capture_" + name)
+    m = g["meta"]
+    mod = m["mod"]
+    if mod not in ("ASK", "FSK"):
+        pytest.skip("ASK/FSK only")
+    qad, center = AI.demod_detect_center(g["iq"], float(g["noise"]), mod)
+    assert bits_equal(qad.get(), g["qad_" + mod]) == 0
+    two_step = AI.detect_center(g["qad_" + mod])
+    assert (center is None) == (two_step is None)
+    gc = float(g["detect_center"])
+    if center is not None:
+        # same bins; the double sums are folded in a different order, so allow the last bits of the variance to move
+        assert abs(center - two_step) <= 1e-9 * max(1.0, abs(two_step))
+        assert abs(center - gc) <= 2e-6 * max(1.0, abs(gc))
+
+
+@pytest.mark.parametrize("n", [3, 2047, 2048, 2049, 70001, 1 << 20])
+@pytest.mark.parametrize("max_size", [None, 5000])
+def test_demod_detect_center_sizes(AI, n, max_size):
+    from urh_b200.cythonext import signal_functions as sf
+    iq = synth_fsk(n, seed=n)
+    qad, center = AI.demod_detect_center(iq, 0.05, "FSK", max_size)
+    ref_qad = sf.afp_demod(iq, 0.05, "FSK", 2)
+    assert bits_equal(qad.get(), ref_qad) == 0
+    two_step = AI.detect_center(ref_qad, max_size)
+    assert (center is None) == (two_step is None)
+    if center is not None:
+        assert abs(center - two_step) <= 1e-9 * max(1.0, abs(two_step))
+
+
+def test_demod_center_digitize_matches_three_calls(AI):
+    from urh_b200.cythonext import signal_functions as sf
+    iq = synth_fsk(1 << 20, seed=5)
+    center, rows = sf.demod_center_digitize(iq, 0.05, "FSK", 5, 100)
+    qad = sf.afp_demod(iq, 0.05, "FSK", 2)
+    c2 = AI.detect_center(qad)
+    assert abs(center - c2) <= 1e-9
+    c2 = center
+    assert np.array_equal(rows, sf.grab_pulse_lens(qad, c2, 5, "FSK", 100))
+    assert rows[:, 1].sum() == len(iq) - 5

@@ -83,6 +83,9 @@ SIGNATURES = {
     "urh_noise_chunk_stats": (i32, [vp, vp, i32, i64, i64, i32, vp, vp]),
     "urh_center_stats": (i32, [vp, vp, i64, i64, vp]),
     "urh_center_histogram": (i32, [vp, vp, i64, i64, i64, C.c_double, C.c_double, i64, vp]),
+    "urh_afp_demod_tiles": (i32, [vp, vp, i32, i64, f32, i32, vp, i32, vp]),
+    "urh_center_window_stats": (i32, [vp, vp, i64, i64, i64, vp]),
+    "urh_center_histogram_tiles": (i32, [vp, vp, i64, i64, i64, C.c_double, C.c_double, i64, vp]),
     "urh_segment_messages": (i32, [vp, vp, i32, i64, f32, vp, i64, C.POINTER(i64)]),
     "urh_plateau_lengths": (i32, [vp, vp, i64, f32, i32, vp, i64, C.POINTER(i64)]),
     "urh_median_filter": (i32, [vp, vp, i64, C.c_uint, vp]),

@@ -194,6 +194,12 @@ def detect_center(rectangular_signal, max_size=None):
     st = np.zeros(7, dtype=np.float64)
     ctx.check(ctx.lib.urh_center_stats(ctx.handle, C.c_void_p(d.ptr), n, -1 if max_size is None else int(max_size),
                                        st.ctypes.data_as(C.c_void_p)))
+    return _center_from_stats(ctx, d, n, st, ctx.lib.urh_center_histogram)
+
+
+def center_bin_edges(st):
+    """detect_center's bin edges (AutoInterpretation.py:206-211): np.arange(min, max + var, var) of the trimmed window;
+    None when the window is empty or constant."""
     r0, r1 = int(st[1]), int(st[2])
     if r1 <= r0:
         return None
@@ -206,11 +212,13 @@ def detect_center(rectangular_signal, max_size=None):
             raise ValueError("need at least two bin edges")
     except (ZeroDivisionError, ValueError):
         return None  # constant segment: no center
+    return edges
+
+
+def pick_center_from_histogram(y, edges):
+    """Peak picking of detect_center (AutoInterpretation.py:213-240): the two most populated bins that dominate their
+    5 % neighbourhood; center = mean of their left edges."""
     nbins = len(edges) - 1
-    y = np.zeros(nbins, dtype=np.int64)
-    # np.arange fills start + i*delta with delta = (start + step) - start
-    ctx.check(ctx.lib.urh_center_histogram(ctx.handle, C.c_void_p(d.ptr), n, r0, r1, C.c_double(edges[0]),
-                                           C.c_double(edges[1] - edges[0]), nbins, y.ctypes.data_as(C.c_void_p)))
     window = max(2, int(0.05 * nbins) + 1)
     levels = []
     for index in np.argsort(y)[::-1]:
@@ -229,6 +237,69 @@ def detect_center(rectangular_signal, max_size=None):
     if len(levels) == 0:
         return None
     return np.mean(levels)
+
+
+def _center_from_stats(ctx, d, n, st, histogram_entry):
+    """Host half of detect_center: bin edges from the trimmed min/max/variance, the device histogram, peak picking."""
+    edges = center_bin_edges(st)
+    if edges is None:
+        return None
+    r0, r1 = int(st[1]), int(st[2])
+    nbins = len(edges) - 1
+    y = np.zeros(nbins, dtype=np.int64)
+    # np.arange fills start + i*delta with delta = (start + step) - start
+    ctx.check(histogram_entry(ctx.handle, C.c_void_p(d.ptr), n, r0, r1, C.c_double(edges[0]),
+                              C.c_double(edges[1] - edges[0]), nbins, y.ctypes.data_as(C.c_void_p)))
+    return pick_center_from_histogram(y, edges)
+
+
+def demod_detect_center(iq, noise_mag: float, mod_type: str, max_size=None, out=None):
+    """afp_demod (ASK/FSK) + detect_center sharing ONE pass over the IQ samples: the demodulator leaves per-tile
+    {count, min, max, sum, sumsq} of the kept samples, so detect_center only adds its histogram pass over qad.
+    Returns (qad DeviceArray, center or None); same values as afp_demod followed by detect_center.
+    ``out``: optional float32[n] DeviceArray to receive qad."""
+    from urh_b200.cythonext.signal_functions import _check_iq
+    iq = _check_iq(iq)
+    on_device = isinstance(iq, DeviceArray)
+    ctx = iq.ctx if on_device else _lib.default_context()
+    n = len(iq)
+    code = _lib.demod_mod_code(mod_type)
+    if code not in (_lib.MOD_ASK, _lib.MOD_FSK) or n <= 2:
+        raise ValueError("demod_detect_center handles ASK and FSK captures of more than 2 samples")
+    d_iq = iq if on_device else to_device(iq, ctx)
+    if out is not None and (not isinstance(out, DeviceArray) or out.dtype != np.float32 or out.shape != (n,)):
+        raise ValueError("out must be a float32 DeviceArray of n samples")
+    qad = out if out is not None else DeviceArray(ctx, (n,), np.float32)
+    kept = C.c_int64(0)
+    ctx.check(ctx.lib.urh_afp_demod_tiles(ctx.handle, C.c_void_p(d_iq.ptr), _lib.dtype_code(d_iq.dtype), n, float(noise_mag),
+                                          code, C.c_void_p(qad.ptr), 0, C.byref(kept)))
+    r0, r1 = center_rank_window(kept.value, max_size)
+    w = np.zeros(5, dtype=np.float64)
+    ctx.check(ctx.lib.urh_center_window_stats(ctx.handle, C.c_void_p(qad.ptr), n, r0, r1, w.ctypes.data_as(C.c_void_p)))
+    st = center_stats_from_window(kept.value, r0, r1, w)
+    return qad, _center_from_stats(ctx, qad, n, st, ctx.lib.urh_center_histogram_tiles)
+
+
+def center_rank_window(kept: int, max_size=None):
+    """detect_center's trimming (AutoInterpretation.py:196-200): ranks [5 %, 95 %) of the kept samples, capped by max_size."""
+    r0, r1 = int(0.05 * kept), int(0.95 * kept)
+    if max_size is not None and r1 - r0 > int(max_size):
+        r1 = r0 + int(max_size)
+    return r0, r1
+
+
+def center_stats_from_window(kept, r0, r1, w):
+    """{count, min, max, sum, sumsq} of the window -> the 7-slot layout urh_center_stats returns."""
+    st = np.zeros(7, dtype=np.float64)
+    st[0], st[1], st[2] = kept, r0, r1
+    cnt = int(w[0])
+    if cnt <= 0:
+        st[2] = st[1]  # empty window: no center
+        return st
+    mean = w[3] / cnt
+    ss = max(0.0, w[4] - cnt * mean * mean)
+    st[3], st[4], st[5], st[6] = w[1], w[2], mean, ss / cnt
+    return st
 
 
 # ---- plateau bookkeeping (AutoInterpretation.py:280-370) ---------------------------------------------------------------

@@ -54,6 +54,9 @@ struct urh_ctx {
     void* shard_state;
     // NCCL (nccl.cu)
     int64_t costas_stats[3];
+    const void* center_ts;
+    int64_t center_n;
+    void* center_prefix;  // tile rank prefix left by urh_afp_demod_stats for urh_center_histogram_tiles (arena)
     void* nccl_comm;
     void* nccl_stage;
     int nccl_rank, nccl_world;

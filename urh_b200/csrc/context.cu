@@ -30,6 +30,7 @@ extern "C" int urh_ctx_create(int device, urh_ctx** out) {
     ctx->shard_tiles = nullptr;
     ctx->shard_staging = nullptr;
     ctx->shard_state = nullptr;
+    ctx->center_prefix = nullptr;
     ctx->nccl_comm = nullptr;
     ctx->nccl_stage = nullptr;
     ctx->nccl_rank = 0;

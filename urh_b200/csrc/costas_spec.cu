@@ -115,7 +115,7 @@ __device__ __forceinline__ int cs_run(const void* iq, int64_t a, int64_t b, CsSt
 template <int DT>
 __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ iq, int64_t n, CsParams P, int64_t nchunks,
                                                       float* __restrict__ cand, CsState* __restrict__ ckpt,
-                                                      int* __restrict__ nonnoise, int first_shard) {
+                                                      int* __restrict__ nonnoise, int* __restrict__ chunk_cnt, int first_shard) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (c >= nchunks) return;
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ i
         cs_run<DT, false>(iq, w0, p0, s, P, nullptr, 0);
     }
     ck[0] = s;
+    int total = 0;
     for (int j = 0; j < P.segs; j++) {
         const int64_t a = p0 + (int64_t)j * CS_SEG;
         int64_t a0 = a;
@@ -145,8 +146,10 @@ __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ i
         const int64_t b0 = min(a + (int64_t)CS_SEG, n);
         const int cnt = cs_run<DT, true>(iq, a0, b0, s, P, out, 0);
         ck[j + 1] = s;
+        total += cnt;
         if (k == 0) nonnoise[c * P.segs + j] = cnt;
     }
+    if (k == 0) chunk_cnt[c] = total;
 }
 
 // pass 2: the chain.  src[c*CS_SEGS + j]: candidate index whose samples are the true ones in that segment, or 255
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ i
 template <int DT>
 __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, int64_t n, CsParams P, int64_t nchunks, int nbr,
                                                    const CsState* __restrict__ ckpt, const int* __restrict__ nonnoise,
-                                                   float* __restrict__ out, uint8_t* __restrict__ src,
+                                                   const int* __restrict__ chunk_cnt, float* __restrict__ out, uint8_t* __restrict__ src,
                                                    int64_t* __restrict__ stats, int first_shard, CsState st_in,
                                                    CsState* __restrict__ st_out) {
     const int lane = threadIdx.x;
@@ -177,9 +180,11 @@ __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, 
                 s0[k].freq = s0[k].phase = s1[k].freq = s1[k].phase = __int_as_float(0x7fc00000);
             }
         }
+        const int my_cnt = (cl < nchunks) ? chunk_cnt[cl] : 0;
         const int todo = (int)min((int64_t)32, nchunks - c0);
         for (int t = 0; t < todo; t++) {
             const int64_t c = c0 + t;
+            const int ccnt = __shfl_sync(URH_FULL_MASK, my_cnt, t);
             int match = -1;
             CsState e;
             e.freq = e.phase = 0.f;
@@ -197,6 +202,11 @@ __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, 
             if (match >= 0) {  // O(1): the candidate's run is the true run
                 if (lane < P.segs) src[c * P.segs + lane] = (uint8_t)match;
                 st = e;
+                fast++;
+                continue;
+            }
+            if (ccnt == 0) {  // all-noise chunk: the loop state is frozen, every candidate holds NOISE
+                if (lane < P.segs) src[c * P.segs + lane] = 0;
                 fast++;
                 continue;
             }
@@ -309,6 +319,7 @@ struct CsRun {
     float* cand;
     CsState* ckpt;
     int* nonnoise;
+    int* chunk_cnt;
     uint8_t* src;
     int64_t* stats;
     CsState* st_out;
@@ -328,26 +339,27 @@ static int cs_speculate(urh_ctx* ctx, CsRun& R) {
     URH_CHECK(urh_arena(ctx, (size_t)R.nbr * R.nchunks * (R.P.segs + 1), &R.ckpt));
     URH_CHECK(urh_arena(ctx, (size_t)R.nchunks * R.P.segs, &R.nonnoise));
     URH_CHECK(urh_arena(ctx, (size_t)R.nchunks * R.P.segs, &R.src));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nchunks, &R.chunk_cnt));
     URH_CHECK(urh_arena(ctx, 4, &R.stats));
     URH_CHECK(urh_arena(ctx, 2, &R.st_out));
     const dim3 grid((unsigned)urh_div_up(R.nchunks, 128), (unsigned)R.nbr);
     switch (R.dtype) {
-        case URH_DT_I8: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_I8>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.first_shard); break;
-        case URH_DT_U8: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_U8>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.first_shard); break;
-        case URH_DT_I16: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_I16>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.first_shard); break;
-        case URH_DT_U16: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_U16>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.first_shard); break;
-        default: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_F32>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.first_shard); break;
+        case URH_DT_I8: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_I8>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard); break;
+        case URH_DT_U8: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_U8>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard); break;
+        case URH_DT_I16: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_I16>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard); break;
+        case URH_DT_U16: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_U16>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard); break;
+        default: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_F32>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard); break;
     }
     return URH_OK;
 }
 
 static int cs_resolve(urh_ctx* ctx, CsRun& R, CsState st_in, float* h_state_out) {
     switch (R.dtype) {
-        case URH_DT_I8: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_I8>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
-        case URH_DT_U8: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_U8>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
-        case URH_DT_I16: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_I16>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
-        case URH_DT_U16: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_U16>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
-        default: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_F32>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
+        case URH_DT_I8: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_I8>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
+        case URH_DT_U8: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_U8>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
+        case URH_DT_I16: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_I16>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
+        case URH_DT_U16: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_U16>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
+        default: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_F32>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
     }
     const unsigned ga = (unsigned)min(urh_div_up(R.n, 256), (int64_t)ctx->sm_count * 32);
     URH_LAUNCH(ctx, k_cs_assemble, ga, 256, 0, R.cand, R.n, R.src, R.out);

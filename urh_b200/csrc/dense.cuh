@@ -35,6 +35,46 @@ struct __align__(16) UrhTileSummary {
     int32_t ncand;      // interior candidates written to the staging area
 };
 
+// Per-tile statistics of the demodulated samples that detect_center keeps (rect > -4, AutoInterpretation.py:227):
+// produced by the dense pass so that the center histogram is the only extra pass over qad.
+struct __align__(16) UrhTileStats {
+    double sum, sumsq;
+    float mn, mx;
+    int32_t cnt, pad;
+};
+
+struct UrhStatAcc {
+    double sum, sumsq;
+    float mn, mx;
+    int cnt;
+    __device__ __forceinline__ void init() { sum = 0.0; sumsq = 0.0; mn = INFINITY; mx = -INFINITY; cnt = 0; }
+    __device__ __forceinline__ void add(float v) {
+        if (v > -4.0f) {
+            const double d = (double)v;
+            sum += d;
+            sumsq += d * d;
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+            cnt++;
+        }
+    }
+    // warp reduction, lane 0 writes
+    __device__ __forceinline__ void store(UrhTileStats* out, int lane) {
+        for (int off = 16; off > 0; off >>= 1) {
+            sum += __shfl_down_sync(URH_FULL_MASK, sum, off);
+            sumsq += __shfl_down_sync(URH_FULL_MASK, sumsq, off);
+            mn = fminf(mn, __shfl_down_sync(URH_FULL_MASK, mn, off));
+            mx = fmaxf(mx, __shfl_down_sync(URH_FULL_MASK, mx, off));
+            cnt += __shfl_down_sync(URH_FULL_MASK, cnt, off);
+        }
+        if (lane == 0) {
+            UrhTileStats t;
+            t.sum = sum; t.sumsq = sumsq; t.mn = mn; t.mx = mx; t.cnt = cnt; t.pad = 0;
+            *out = t;
+        }
+    }
+};
+
 // ---- IQ sample access ------------------------------------------------------------------------------
 template <int DT> struct UrhElem;
 template <> struct UrhElem<URH_DT_I8> { typedef int8_t type; };

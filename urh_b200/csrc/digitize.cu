@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32)
 k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __restrict__ qad_out, int vec_in,
            int vec_out, const __grid_constant__ UrhClassify cls, int tol, UrhTileSummary* __restrict__ tiles,
            uint32_t* __restrict__ staging, int stage_cap, int16_t* __restrict__ init_cls, int cls_of_zero,
-           int64_t tile_begin, int64_t tile_count, int has_halo) {
+           int64_t tile_begin, int64_t tile_count, int has_halo, UrhTileStats* __restrict__ tile_stats) {
     const int lane = threadIdx.x & 31;
     const int64_t tile_rel = (int64_t)blockIdx.x * URH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (tile_rel >= tile_count) return;
@@ -35,6 +35,8 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
 
     UrhRunTracker rt;
     if (DIGITIZE) rt.init(tol, staging + tile * (int64_t)stage_cap);
+    UrhStatAcc acc;
+    acc.init();
 
     // FSK: (A, B) terms of the sample preceding the tile's first sample
     float cA = 0.0f, cB = 0.0f;
@@ -73,6 +75,10 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
         if (pos0 == 0 && !has_halo) s0 = dp.noise_value;  // result[0] = NOISE (pyx:361); shards: only the capture's first sample
 
         const bool v0 = pos0 < n, v1 = pos0 + 1 < n;
+        if (tile_stats) {
+            if (v0) acc.add(s0);
+            if (v1) acc.add(s1);
+        }
         if (qad_out) {
             if (v1 && vec_out) urh_stg_f2(qad_out + pos0, s0, s1);
             else {
@@ -87,16 +93,17 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
         }
         cur = nxt;
     }
+    if (tile_stats) acc.store(tile_stats + tile, lane);
     if (DIGITIZE) rt.finish(tile_len, tiles + tile, lane);
 }
 
 // Fast kernel: full, aligned, order-2 FSK tiles [tile_begin, tile_begin + tile_count), tile_begin >= 1
 // (fsk_fast.cuh: packed f32x2 math, same bits as the generic kernel).
-template <int DT, bool DIGITIZE, bool WRITE>
+template <int DT, bool DIGITIZE, bool WRITE, bool STATS>
 __global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32, URH_FAST_MIN_BLOCKS)
 k_fsk_fast(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __restrict__ qad_out, float thr0,
            float cls_noise, int tol, UrhTileSummary* __restrict__ tiles, uint32_t* __restrict__ staging, int stage_cap,
-           int64_t tile_begin, int64_t tile_count) {
+           int64_t tile_begin, int64_t tile_count, UrhTileStats* __restrict__ tile_stats) {
     const int lane = threadIdx.x & 31;
     const int64_t tile_rel = (int64_t)blockIdx.x * URH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (tile_rel >= tile_count) return;
@@ -106,7 +113,8 @@ k_fsk_fast(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
     UrhOne one;
     one.p = dp.one;
     one.m = dp.mone;
-    urh_fsk_full_tile<DT, DIGITIZE, WRITE>(iq, n, tile * URH_TILE, dp, qad_out, thr0, cls_noise, rt, lane, one);
+    urh_fsk_full_tile<DT, DIGITIZE, WRITE, STATS>(iq, n, tile * URH_TILE, dp, qad_out, thr0, cls_noise, rt, lane, one,
+                                                  STATS ? tile_stats + tile : nullptr);
     if (DIGITIZE) rt.finish(URH_TILE, tiles + tile, lane);
 }
 
@@ -161,7 +169,8 @@ static bool iq_vec_aligned(const void* p, int dtype) { return ((uintptr_t)p % (2
 template <int DT, int MOD, bool DIG>
 static int launch_dense_iq_t(urh_ctx* ctx, const void* d_iq, int64_t n, const UrhDemodParams& dp, float* d_qad,
                              const UrhClassify& cls, int tol, UrhTileSummary* tiles, uint32_t* staging,
-                             int stage_cap, int16_t* init_cls, int cls_of_zero, int has_halo = 0) {
+                             int stage_cap, int16_t* init_cls, int cls_of_zero, int has_halo = 0,
+                             UrhTileStats* tile_stats = nullptr) {
     const int64_t ntiles = urh_div_up(n, URH_TILE);
     const int vec_in = iq_vec_aligned(d_iq, DT) ? 1 : 0;
     const int vec_out = (d_qad && ((uintptr_t)d_qad % 8) == 0) ? 1 : 0;
@@ -169,7 +178,8 @@ static int launch_dense_iq_t(urh_ctx* ctx, const void* d_iq, int64_t n, const Ur
     auto generic = [&](int64_t begin, int64_t count) -> int {
         if (count <= 0) return URH_OK;
         URH_LAUNCH(ctx, (k_dense_iq<DT, MOD, DIG>), (unsigned)urh_div_up(count, URH_WARPS_PER_BLOCK), threads, 0, d_iq, n, dp,
-                   d_qad, vec_in, vec_out, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, begin, count, has_halo);
+                   d_qad, vec_in, vec_out, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, begin, count, has_halo,
+                   tile_stats);
         return URH_OK;
     };
     // FSK on aligned buffers with a binary digitizer: tiles 1 .. nfull-1 take the packed-f32x2 kernel
@@ -178,12 +188,15 @@ static int launch_dense_iq_t(urh_ctx* ctx, const void* d_iq, int64_t n, const Ur
     URH_PROF_BEGIN(ctx);
     if (fast) {
         const unsigned grid = (unsigned)urh_div_up(nfull - 1, URH_WARPS_PER_BLOCK);
-        if (d_qad)
-            URH_LAUNCH(ctx, (k_fsk_fast<DT, DIG, true>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
-                       tiles, staging, stage_cap, (int64_t)1, nfull - 1);
+        if (tile_stats && d_qad && !DIG)
+            URH_LAUNCH(ctx, (k_fsk_fast<DT, false, true, true>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value,
+                       tol, tiles, staging, stage_cap, (int64_t)1, nfull - 1, tile_stats);
+        else if (d_qad)
+            URH_LAUNCH(ctx, (k_fsk_fast<DT, DIG, true, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
+                       tiles, staging, stage_cap, (int64_t)1, nfull - 1, nullptr);
         else
-            URH_LAUNCH(ctx, (k_fsk_fast<DT, DIG, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
-                       tiles, staging, stage_cap, (int64_t)1, nfull - 1);
+            URH_LAUNCH(ctx, (k_fsk_fast<DT, DIG, false, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
+                       tiles, staging, stage_cap, (int64_t)1, nfull - 1, nullptr);
         URH_CHECK(generic(0, 1));
         URH_CHECK(generic(nfull, ntiles - nfull));
     } else {
@@ -196,13 +209,14 @@ static int launch_dense_iq_t(urh_ctx* ctx, const void* d_iq, int64_t n, const Ur
 template <int MOD, bool DIG>
 static int launch_dense_iq_m(urh_ctx* ctx, int dtype, const void* d_iq, int64_t n, const UrhDemodParams& dp,
                              float* d_qad, const UrhClassify& cls, int tol, UrhTileSummary* tiles,
-                             uint32_t* staging, int stage_cap, int16_t* init_cls, int cls_of_zero, int has_halo = 0) {
+                             uint32_t* staging, int stage_cap, int16_t* init_cls, int cls_of_zero, int has_halo = 0,
+                             UrhTileStats* tile_stats = nullptr) {
     switch (dtype) {
-        case URH_DT_I8: return launch_dense_iq_t<URH_DT_I8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo);
-        case URH_DT_U8: return launch_dense_iq_t<URH_DT_U8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo);
-        case URH_DT_I16: return launch_dense_iq_t<URH_DT_I16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo);
-        case URH_DT_U16: return launch_dense_iq_t<URH_DT_U16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo);
-        case URH_DT_F32: return launch_dense_iq_t<URH_DT_F32, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo);
+        case URH_DT_I8: return launch_dense_iq_t<URH_DT_I8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats);
+        case URH_DT_U8: return launch_dense_iq_t<URH_DT_U8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats);
+        case URH_DT_I16: return launch_dense_iq_t<URH_DT_I16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats);
+        case URH_DT_U16: return launch_dense_iq_t<URH_DT_U16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats);
+        case URH_DT_F32: return launch_dense_iq_t<URH_DT_F32, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats);
         default: URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
     }
 }
@@ -244,6 +258,33 @@ extern "C" int urh_afp_demod(urh_ctx* ctx, const void* d_iq, int dtype, int64_t 
     if (mod_type == URH_MOD_ASK)
         return launch_dense_iq_m<URH_MOD_ASK, false>(ctx, dtype, d_iq, n, dp, d_out, cls, 0, nullptr, nullptr, 0, nullptr, 0);
     return launch_dense_iq_m<URH_MOD_FSK, false>(ctx, dtype, d_iq, n, dp, d_out, cls, 0, nullptr, nullptr, 0, nullptr, 0);
+}
+
+int urh_center_tiles_begin(urh_ctx* ctx, const UrhTileStats* ts, int64_t n, int64_t* h_total);  // stats.cu
+
+// afp_demod (ASK / FSK) that also collects, in the same pass over the IQ samples, what detect_center needs: per-tile
+// {count, min, max, sum, sumsq} of the samples it keeps (> -4).  *h_kept = number of kept samples.  The table stays in
+// the ctx arena for urh_center_window_stats / urh_center_histogram_tiles (any other ctx call invalidates it).
+// halo = 1: the sample preceding d_iq (the previous shard's last) is readable right before it, so qad[0] is a real value
+// instead of the capture-start NOISE sentinel.
+extern "C" int urh_afp_demod_tiles(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_mag, int mod_type,
+                                   float* d_qad_out, int halo, int64_t* h_kept) {
+    if (n <= 2 || (mod_type != URH_MOD_ASK && mod_type != URH_MOD_FSK) || !d_qad_out)
+        URH_FAIL(ctx, URH_ERR_INVALID, "urh_afp_demod_tiles: ASK/FSK, n > 2 and a qad buffer are required");
+    if (urh_iq_bytes(dtype) == 0) URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
+    urh_arena_reset(ctx);
+    ctx->center_prefix = nullptr;
+    const UrhDemodParams dp = make_demod_params(noise_mag, mod_type, dtype);
+    UrhClassify cls;
+    memset(&cls, 0, sizeof(cls));
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    UrhTileStats* ts;
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles, &ts));
+    if (mod_type == URH_MOD_ASK)
+        URH_CHECK((launch_dense_iq_m<URH_MOD_ASK, false>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, 0, nullptr, nullptr, 0, nullptr, 0, halo, ts)));
+    else
+        URH_CHECK((launch_dense_iq_m<URH_MOD_FSK, false>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, 0, nullptr, nullptr, 0, nullptr, 0, halo, ts)));
+    return urh_center_tiles_begin(ctx, ts, n, h_kept);
 }
 
 // Shared tail of the two digitizer entry points: tile table + staging -> merged (state, length) rows.

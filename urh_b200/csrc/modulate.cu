@@ -63,10 +63,12 @@ __global__ void k_fsk_corrections(const uint8_t* __restrict__ bits, const int64_
     }
 }
 
-// GFSK: Gaussian-filtered per-sample frequencies ('same' convolution, double accumulation, float32 result)
+// GFSK: Gaussian-filtered per-sample frequencies ('same' convolution of the piecewise-constant symbol frequencies).
+// The frequency is constant over a symbol, so c[t] = sum_j freq[t-j] g[j] collapses to one term per symbol the window
+// touches: f_sym * (G[hi] - G[lo]) with G the running sum of the taps (double) — ~3 terms instead of 2*sps+1.
 __global__ void k_gfsk_freqs(const uint8_t* __restrict__ bits, const int64_t* __restrict__ bit_off,
                              const int64_t* __restrict__ smp_off, int nmsg, const __grid_constant__ ModParams P,
-                             const float* __restrict__ gfir, int glen, float* __restrict__ fp_table) {
+                             const double* __restrict__ gsum /* glen+1 prefix sums */, int glen, float* __restrict__ fp_table) {
     const int m = blockIdx.y;
     const uint8_t* b = bits + bit_off[m];
     const int64_t nsym = (bit_off[m + 1] - bit_off[m]) / P.bps;
@@ -74,21 +76,21 @@ __global__ void k_gfsk_freqs(const uint8_t* __restrict__ bits, const int64_t* __
     float* out = fp_table + 2 * smp_off[m];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nval; k += stride) {
+        // np.convolve(longer, shorter, 'same'): centred on the longer operand
+        const int64_t t = (nval >= glen) ? k + (glen - 1) / 2 : k + (nval - 1) / 2;
+        // c[t] = sum over i in [max(0, t-glen+1), min(nval-1, t)] of freq[i] * g[t-i]
+        int64_t ilo = t - (glen - 1), ihi = t;
+        if (ilo < 0) ilo = 0;
+        if (ihi > nval - 1) ihi = nval - 1;
         double acc = 0.0;
-        if (nval >= glen) {
-            // np.convolve(freq, gfir, 'same'): c[t] = sum_j freq[t-j]*g[j], t = k + (glen-1)/2
-            const int64_t t = k + (glen - 1) / 2;
-            for (int j = 0; j < glen; j++) {
-                const int64_t i = t - j;
-                if (i >= 0 && i < nval) acc += (double)P.params[symbol_index(b, i / P.sps, P.bps)] * (double)gfir[j];
-            }
-        } else {
-            // np.convolve(gfir, freq, 'same')[:nval]: centred on the (longer) filter
-            const int64_t t = k + (nval - 1) / 2;
-            for (int64_t i = 0; i < nval; i++) {
-                const int64_t j = t - i;
-                if (j >= 0 && j < glen) acc += (double)P.params[symbol_index(b, i / P.sps, P.bps)] * (double)gfir[j];
-            }
+        for (int64_t i = ilo; i <= ihi;) {
+            const int64_t sidx = i / P.sps;
+            int64_t iend = (sidx + 1) * (int64_t)P.sps - 1;  // last sample of this symbol
+            if (iend > ihi) iend = ihi;
+            // taps j = t - i for i in [i, iend]  ->  j in [t - iend, t - i]
+            const double w = gsum[t - i + 1] - gsum[t - iend];
+            acc += (double)P.params[symbol_index(b, sidx, P.bps)] * w;
+            i = iend + 1;
         }
         out[2 * k] = (float)acc;
     }
@@ -217,7 +219,8 @@ extern "C" int urh_modulate_batch(urh_ctx* ctx, const uint8_t* d_bits, const int
     URH_CUDA(ctx, cudaMemcpyAsync(d_out_off, h_out_off, ob, cudaMemcpyHostToDevice, ctx->stream));
     const size_t elem = out_dtype == URH_DT_F32 ? 4 : (out_dtype == URH_DT_I16 ? 2 : 1);
     URH_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)h_out_off[nmsg] * 2 * elem, ctx->stream));
-    float *corr = nullptr, *fp_table = nullptr, *d_gfir = nullptr;
+    float *corr = nullptr, *fp_table = nullptr;
+    double* d_gsum = nullptr;
     if (mod_type == URH_MOD_FSK) {
         URH_CHECK(urh_arena(ctx, (size_t)sym_off[nmsg] + 1, &corr));
         URH_LAUNCH(ctx, k_fsk_corrections, (unsigned)urh_div_up(nmsg, 64), 64, 0, d_bits, d_bit_off, d_sym_off, nmsg, P, corr);
@@ -227,9 +230,12 @@ extern "C" int urh_modulate_batch(urh_ctx* ctx, const uint8_t* d_bits, const int
     if (mod_type == URH_MOD_GFSK) {
         if (!h_gauss_fir || gauss_len <= 0) URH_FAIL(ctx, URH_ERR_INVALID, "GFSK needs the gaussian filter taps");
         URH_CHECK(urh_arena(ctx, (size_t)smp_off[nmsg] * 2 + 2, &fp_table));
-        URH_CHECK(urh_arena(ctx, (size_t)gauss_len, &d_gfir));
-        URH_CUDA(ctx, cudaMemcpyAsync(d_gfir, h_gauss_fir, gauss_len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        URH_LAUNCH(ctx, k_gfsk_freqs, grid, 256, 0, d_bits, d_bit_off, d_smp_off, nmsg, P, d_gfir, gauss_len, fp_table);
+        std::vector<double> gsum((size_t)gauss_len + 1, 0.0);
+        for (int j = 0; j < gauss_len; j++) gsum[j + 1] = gsum[j] + (double)h_gauss_fir[j];
+        URH_CHECK(urh_arena(ctx, (size_t)gauss_len + 1, &d_gsum));
+        URH_CUDA(ctx, cudaMemcpyAsync(d_gsum, gsum.data(), (gauss_len + 1) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        URH_LAUNCH(ctx, k_gfsk_freqs, grid, 256, 0, d_bits, d_bit_off, d_smp_off, nmsg, P, d_gsum, gauss_len, fp_table);
         URH_LAUNCH(ctx, k_gfsk_phases, (unsigned)urh_div_up(nmsg, 64), 64, 0, d_bit_off, d_smp_off, nmsg, P, fp_table);
     }
     if (out_dtype == URH_DT_F32)

@@ -539,3 +539,272 @@ extern "C" int urh_arr2decibel(urh_ctx* ctx, const float* d_complex, int64_t cou
     URH_LAUNCH(ctx, k_decibel, grid, 256, 0, (const float2*)d_complex, count, d_out);
     return URH_OK;
 }
+
+// =====================================================================================================
+// detect_center fed by the dense pass: the demodulator already produced per-tile {count, min, max, sum, sumsq} of the
+// samples detect_center keeps (UrhTileStats), so the trimmed statistics need no pass over qad at all (only the two
+// tiles that contain the 5 % / 95 % rank cuts are re-read) and the histogram is the single extra pass.
+// =====================================================================================================
+__global__ void k_tile_counts(const UrhTileStats* __restrict__ ts, int64_t ntiles, int64_t* __restrict__ prefix) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntiles) prefix[t] = ts[t].cnt;
+}
+
+// rank-exact partial statistics of one tile (used for the <= 2 tiles cut by the rank window); one block per listed tile
+__global__ void __launch_bounds__(256) k_edge_tile_stats(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ prefix,
+                                                        const int64_t* __restrict__ edge_tiles, int64_t r0, int64_t r1,
+                                                        CenStats* __restrict__ out) {
+    const int64_t t = edge_tiles[blockIdx.x];
+    CenStats o;
+    o.sum = 0.0; o.sumsq = 0.0; o.mn = INFINITY; o.mx = -INFINITY; o.cnt = 0;
+    if (t >= 0) {
+        const int per = URH_TILE / 256;
+        const int64_t base = t * URH_TILE + (int64_t)threadIdx.x * per;
+        float v[per];
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < per; j++) {
+            v[j] = (base + j < n) ? x[base + j] : -5.0f;
+            mine += (v[j] > -4.0f) ? 1 : 0;
+        }
+        __shared__ int s_pre[256];
+        s_pre[threadIdx.x] = mine;
+        __syncthreads();
+        for (int off = 1; off < 256; off <<= 1) {
+            int add = 0;
+            if (threadIdx.x >= off) add = s_pre[threadIdx.x - off];
+            __syncthreads();
+            s_pre[threadIdx.x] += add;
+            __syncthreads();
+        }
+        int64_t rank = prefix[t] + s_pre[threadIdx.x] - mine;
+#pragma unroll
+        for (int j = 0; j < per; j++) {
+            if (v[j] > -4.0f) {
+                if (rank >= r0 && rank < r1) {
+                    o.sum += (double)v[j];
+                    o.sumsq += (double)v[j] * (double)v[j];
+                    o.mn = fminf(o.mn, v[j]);
+                    o.mx = fmaxf(o.mx, v[j]);
+                    o.cnt++;
+                }
+                rank++;
+            }
+        }
+    }
+    __shared__ double s_sum[256], s_sq[256];
+    __shared__ float s_mn[256], s_mx[256];
+    __shared__ long long s_cnt[256];
+    s_sum[threadIdx.x] = o.sum; s_sq[threadIdx.x] = o.sumsq; s_mn[threadIdx.x] = o.mn; s_mx[threadIdx.x] = o.mx; s_cnt[threadIdx.x] = o.cnt;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            s_sum[threadIdx.x] += s_sum[threadIdx.x + off];
+            s_sq[threadIdx.x] += s_sq[threadIdx.x + off];
+            s_mn[threadIdx.x] = fminf(s_mn[threadIdx.x], s_mn[threadIdx.x + off]);
+            s_mx[threadIdx.x] = fmaxf(s_mx[threadIdx.x], s_mx[threadIdx.x + off]);
+            s_cnt[threadIdx.x] += s_cnt[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        CenStats r;
+        r.sum = s_sum[0]; r.sumsq = s_sq[0]; r.mn = s_mn[0]; r.mx = s_mx[0]; r.cnt = s_cnt[0];
+        out[blockIdx.x] = r;
+    }
+}
+
+// interior tiles (entirely inside the rank window): fold the dense pass's partials; grid-stride, one partial per block
+__global__ void __launch_bounds__(256) k_interior_tile_stats(const UrhTileStats* __restrict__ ts, const int64_t* __restrict__ prefix,
+                                                            int64_t ntiles, int64_t r0, int64_t r1, CenStats* __restrict__ partial) {
+    double sum = 0.0, sq = 0.0;
+    float mn = INFINITY, mx = -INFINITY;
+    long long cnt = 0;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < ntiles; t += (int64_t)gridDim.x * 256) {
+        const int64_t a = prefix[t], b = prefix[t + 1];
+        if (b > a && a >= r0 && b <= r1) {
+            const UrhTileStats v = ts[t];
+            sum += v.sum; sq += v.sumsq; mn = fminf(mn, v.mn); mx = fmaxf(mx, v.mx); cnt += v.cnt;
+        }
+    }
+    __shared__ double s_sum[256], s_sq[256];
+    __shared__ float s_mn[256], s_mx[256];
+    __shared__ long long s_cnt[256];
+    s_sum[threadIdx.x] = sum; s_sq[threadIdx.x] = sq; s_mn[threadIdx.x] = mn; s_mx[threadIdx.x] = mx; s_cnt[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            s_sum[threadIdx.x] += s_sum[threadIdx.x + off];
+            s_sq[threadIdx.x] += s_sq[threadIdx.x + off];
+            s_mn[threadIdx.x] = fminf(s_mn[threadIdx.x], s_mn[threadIdx.x + off]);
+            s_mx[threadIdx.x] = fmaxf(s_mx[threadIdx.x], s_mx[threadIdx.x + off]);
+            s_cnt[threadIdx.x] += s_cnt[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        CenStats r;
+        r.sum = s_sum[0]; r.sumsq = s_sq[0]; r.mn = s_mn[0]; r.mx = s_mx[0]; r.cnt = s_cnt[0];
+        partial[blockIdx.x] = r;
+    }
+}
+
+// histogram over the dense pass's tiles: interior tiles need no rank bookkeeping
+__global__ void __launch_bounds__(256) k_hist_tiles(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ prefix,
+                                                   int64_t ntiles, int64_t r0, int64_t r1, double hmin, double hstep, int64_t nbins,
+                                                   unsigned long long* __restrict__ hist, int hist_in_smem) {
+    extern __shared__ unsigned int s_hist[];
+    __shared__ int s_pre[256];
+    if (hist_in_smem) {
+        for (int64_t b = threadIdx.x; b < nbins; b += 256) s_hist[b] = 0u;
+        __syncthreads();
+    }
+    const double last_edge = hmin + (double)nbins * hstep;
+    const double inv = 1.0 / hstep;
+    auto put = [&](float f) {
+        const double a = (double)f;
+        int64_t k = (int64_t)floor((a - hmin) * inv);
+        if (k < 0) k = 0;
+        if (k > nbins - 1) k = nbins - 1;
+        while (k > 0 && a < hmin + (double)k * hstep) k--;
+        while (k < nbins - 1 && a >= hmin + (double)(k + 1) * hstep) k++;
+        if (a >= hmin && a <= last_edge) {
+            if (hist_in_smem) atomicAdd(&s_hist[k], 1u);
+            else atomicAdd(&hist[k], 1ull);
+        }
+    };
+    const int per = URH_TILE / 256;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t a = prefix[t], b = prefix[t + 1];
+        if (b <= a || b <= r0 || a >= r1) continue;  // block-uniform
+        const int64_t base = t * URH_TILE;
+        if (a >= r0 && b <= r1) {
+            // interior: coalesced, every kept sample counts
+            for (int j = threadIdx.x; j < URH_TILE; j += 256) {
+                const int64_t i = base + j;
+                if (i < n) {
+                    const float f = x[i];
+                    if (f > -4.0f) put(f);
+                }
+            }
+        } else {
+            float v[per];
+            int mine = 0;
+#pragma unroll
+            for (int j = 0; j < per; j++) {
+                const int64_t i = base + (int64_t)threadIdx.x * per + j;
+                v[j] = (i < n) ? x[i] : -5.0f;
+                mine += (v[j] > -4.0f) ? 1 : 0;
+            }
+            s_pre[threadIdx.x] = mine;
+            __syncthreads();
+            for (int off = 1; off < 256; off <<= 1) {
+                int add = 0;
+                if (threadIdx.x >= off) add = s_pre[threadIdx.x - off];
+                __syncthreads();
+                s_pre[threadIdx.x] += add;
+                __syncthreads();
+            }
+            int64_t rank = a + s_pre[threadIdx.x] - mine;
+#pragma unroll
+            for (int j = 0; j < per; j++) {
+                if (v[j] > -4.0f) {
+                    if (rank >= r0 && rank < r1) put(v[j]);
+                    rank++;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (hist_in_smem) {
+        __syncthreads();
+        for (int64_t b = threadIdx.x; b < nbins; b += 256)
+            if (s_hist[b]) atomicAdd(&hist[b], (unsigned long long)s_hist[b]);
+    }
+}
+
+// Rank prefix over the tile table the demodulator produced; leaves {ts, prefix, n} in ctx for the window / histogram calls.
+int urh_center_tiles_begin(urh_ctx* ctx, const UrhTileStats* ts, int64_t n, int64_t* h_total) {
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    int64_t *prefix, *d_total;
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles + 1, &prefix));
+    URH_CHECK(urh_arena(ctx, 4, &d_total));
+    URH_LAUNCH(ctx, k_tile_counts, (unsigned)urh_div_up(ntiles, 256), 256, 0, ts, ntiles, prefix);
+    URH_CHECK((urhscan::device_scan<int64_t, urhscan::AddI64>(ctx, prefix, ntiles, urhscan::AddI64(), (int64_t)0, true, d_total)));
+    URH_CUDA(ctx, cudaMemcpyAsync(prefix + ntiles, d_total, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    URH_CHECK(urh_read_i64(ctx, d_total, 1, h_total));
+    ctx->center_prefix = prefix;
+    ctx->center_ts = ts;
+    ctx->center_n = n;
+    return URH_OK;
+}
+
+// {count, min, max, sum, sumsq} of the kept samples whose LOCAL rank is in [r0, r1): interior tiles from the table, the
+// two cut tiles re-read from qad.  A shard passes the global window minus its rank offset (clamped to its own count).
+extern "C" int urh_center_window_stats(urh_ctx* ctx, const float* d_qad, int64_t n, int64_t r0, int64_t r1, double* h_out5) {
+    h_out5[0] = 0.0; h_out5[1] = INFINITY; h_out5[2] = -INFINITY; h_out5[3] = 0.0; h_out5[4] = 0.0;
+    if (!ctx->center_prefix || ctx->center_n != n) URH_FAIL(ctx, URH_ERR_INVALID, "urh_afp_demod_tiles must precede urh_center_window_stats");
+    if (r1 <= r0) return URH_OK;
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    const int64_t* prefix = (const int64_t*)ctx->center_prefix;
+    const UrhTileStats* ts = (const UrhTileStats*)ctx->center_ts;
+    int64_t* d_edges;
+    CenStats* partial;
+    CenStats* folded;
+    const int nb = ctx->sm_count * 2;
+    URH_CHECK(urh_arena(ctx, 4, &d_edges));
+    URH_CHECK(urh_arena(ctx, (size_t)nb + 4, &partial));
+    URH_CHECK(urh_arena(ctx, 2, &folded));
+    // the (at most two) tiles cut by the window: found on the host by bisection over the prefix (tiny read-backs)
+    auto tile_of_rank = [&](int64_t r, int64_t* out_t) -> int {
+        int64_t lo = 0, hi = ntiles;  // largest t with prefix[t] <= r
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) / 2;
+            int64_t v;
+            URH_CHECK(urh_read_i64(ctx, prefix + mid, 1, &v));
+            if (v <= r) lo = mid; else hi = mid;
+        }
+        *out_t = lo;
+        return URH_OK;
+    };
+    int64_t e[2] = {-1, -1};
+    URH_CHECK(tile_of_rank(r0, &e[0]));
+    URH_CHECK(tile_of_rank(r1 - 1, &e[1]));
+    if (e[1] == e[0]) e[1] = -1;
+    // a cut tile is "edge" unless the window covers it completely (then the interior kernel takes it)
+    for (int q = 0; q < 2; q++) {
+        if (e[q] < 0) continue;
+        int64_t ab[2];
+        URH_CHECK(urh_read_i64(ctx, prefix + e[q], 2, ab));
+        if (ab[0] >= r0 && ab[1] <= r1) e[q] = -1;
+    }
+    URH_CUDA(ctx, cudaMemcpyAsync(d_edges, e, sizeof(e), cudaMemcpyHostToDevice, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    URH_LAUNCH(ctx, k_interior_tile_stats, nb, 256, 0, ts, prefix, ntiles, r0, r1, partial);
+    URH_LAUNCH(ctx, k_edge_tile_stats, 2, 256, 0, d_qad, n, prefix, d_edges, r0, r1, partial + nb);
+    URH_LAUNCH(ctx, k_center_fold, 1, 256, 0, partial, (int64_t)nb + 2, folded);
+    CenStats st;
+    URH_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail, folded, sizeof(CenStats), cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(&st, ctx->h_mail, sizeof(st));
+    h_out5[0] = (double)st.cnt; h_out5[1] = (double)st.mn; h_out5[2] = (double)st.mx; h_out5[3] = st.sum; h_out5[4] = st.sumsq;
+    return URH_OK;
+}
+
+// histogram pass that goes with urh_afp_demod_stats (uses the tile prefix it left in the arena)
+extern "C" int urh_center_histogram_tiles(urh_ctx* ctx, const float* d_qad, int64_t n, int64_t r0, int64_t r1, double hmin,
+                                          double hstep, int64_t nbins, int64_t* h_hist) {
+    if (nbins <= 0) return URH_OK;
+    if (!ctx->center_prefix || ctx->center_n != n) URH_FAIL(ctx, URH_ERR_INVALID, "urh_afp_demod_tiles must precede urh_center_histogram_tiles");
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    unsigned long long* hist;
+    URH_CHECK(urh_arena(ctx, (size_t)nbins, &hist));
+    URH_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(unsigned long long), ctx->stream));
+    const int in_smem = nbins <= 12000 ? 1 : 0;
+    const unsigned gs = (unsigned)min(ntiles, (int64_t)ctx->sm_count * 8);
+    URH_LAUNCH(ctx, k_hist_tiles, gs, 256, in_smem ? (size_t)nbins * sizeof(unsigned int) : 0, d_qad, n, (const int64_t*)ctx->center_prefix,
+               ntiles, r0, r1, hmin, hstep, nbins, hist, in_smem);
+    URH_CUDA(ctx, cudaMemcpyAsync(h_hist, hist, (size_t)nbins * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return URH_OK;
+}

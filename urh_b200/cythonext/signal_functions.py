@@ -123,6 +123,23 @@ def demod_digitize(samples, noise_mag: float, mod_type: str, center: float, tole
     return qad, rows
 
 
+def demod_center_digitize(samples, noise_mag: float, mod_type: str, tolerance: int, samples_per_symbol: int,
+                          bits_per_symbol: int = 1, center_spacing: float = 0.1, max_size=None, return_qad: bool = False):
+    """afp_demod -> detect_center -> grab_pulse_lens for a capture whose center is not known yet (ASK/FSK): two passes
+    over the IQ-rate data instead of the reference's five (demod+statistics, histogram of qad, then digitize from qad).
+    Returns (center, int64[k,2]) or (center, rows, qad) with return_qad.  center None -> no pulses (empty table)."""
+    from urh_b200.ainterpretation.AutoInterpretation import demod_detect_center
+    on_device = isinstance(samples, DeviceArray)
+    qad, center = demod_detect_center(samples, noise_mag, mod_type, max_size)
+    if center is None:
+        rows = np.zeros((0, 2), dtype=np.int64)
+    else:
+        rows = grab_pulse_lens(qad, float(center), tolerance, mod_type, samples_per_symbol, bits_per_symbol, center_spacing)
+    if return_qad:
+        return center, rows, (qad if on_device else qad.get())
+    return center, rows
+
+
 # ---- modulator ------------------------------------------------------------------------------------------------
 def get_oqpsk_bits(original_bits) -> np.ndarray:
     """signal_functions.pyx:179-193 (host; a bit shuffle on a few thousand bits)."""

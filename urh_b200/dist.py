@@ -234,6 +234,56 @@ def demod_digitize_distributed(ctx, rank, world, sb: ShardBuffer, global_offset,
     return rows
 
 
+def detect_center_distributed(ctx, rank, world, sb: ShardBuffer, noise_mag, mod_type, d_qad, max_size=None):
+    """afp_demod of the shard into ``d_qad`` + the capture-wide detect_center, every rank ending with the same center.
+    Exchange (NCCL, a few hundred bytes + one histogram): kept-sample counts -> global rank window; per-rank window
+    partials {count, min, max, sum, sumsq} folded in rank order (deterministic) -> bin edges; histogram all-reduce."""
+    from .ainterpretation.AutoInterpretation import center_rank_window, center_stats_from_window, pick_center_from_histogram, \
+        center_bin_edges
+    from .device import DeviceArray
+    lib = ctx.lib
+    code = _lib.demod_mod_code(mod_type)
+    kept = C.c_int64(0)
+    ctx.check(lib.urh_afp_demod_tiles(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, float(noise_mag), code,
+                                      C.c_void_p(d_qad.ptr), int(rank > 0), C.byref(kept)))
+    counts = nccl_allgather_i64(ctx, world, [kept.value])[:, 0]
+    total, offset = int(counts.sum()), int(counts[:rank].sum())
+    r0, r1 = center_rank_window(total, max_size)
+    lr0 = min(max(r0 - offset, 0), kept.value)
+    lr1 = min(max(r1 - offset, 0), kept.value)
+    w = np.zeros(5, dtype=np.float64)
+    ctx.check(lib.urh_center_window_stats(ctx.handle, C.c_void_p(d_qad.ptr), sb.n, lr0, lr1, w.ctypes.data_as(C.c_void_p)))
+    parts = nccl_allgather_i64(ctx, world, w.view(np.int64)).view(np.float64)
+    g = np.array([parts[:, 0].sum(), parts[:, 1].min(), parts[:, 2].max(), 0.0, 0.0])
+    for q in range(world):  # rank order, so every rank (and every world size's replay) folds identically
+        g[3] += parts[q, 3]
+        g[4] += parts[q, 4]
+    st = center_stats_from_window(total, r0, r1, g)
+    edges = center_bin_edges(st)
+    if edges is None:
+        return None
+    nbins = len(edges) - 1
+    y = np.zeros(nbins, dtype=np.int64)
+    ctx.check(lib.urh_center_histogram_tiles(ctx.handle, C.c_void_p(d_qad.ptr), sb.n, lr0, lr1, C.c_double(edges[0]),
+                                             C.c_double(edges[1] - edges[0]), nbins, y.ctypes.data_as(C.c_void_p)))
+    d_hist = DeviceArray(ctx, (nbins,), np.int64)
+    d_hist.set(y)
+    ctx.check(lib.urh_nccl_allreduce_i64(ctx.handle, C.c_void_p(d_hist.ptr), nbins, 0))
+    return pick_center_from_histogram(d_hist.get(), edges)
+
+
+def demod_center_digitize_distributed(ctx, rank, world, sb: ShardBuffer, global_offset, n_total, noise_mag, mod_type, tolerance,
+                                      samples_per_symbol, d_qad, bits_per_symbol=1, center_spacing=0.1, max_size=None, fetch=True):
+    """BASELINE configs[1]/[4] on N GPUs: demod + capture-wide detect_center + digitize of ONE sharded capture.
+    The digitizer pass re-reads the shard's IQ (urh_shard_dense) once the center is known.  -> (center, rows or count)."""
+    center = detect_center_distributed(ctx, rank, world, sb, noise_mag, mod_type, d_qad, max_size)
+    if center is None:
+        return None, (np.zeros((0, 2), dtype=np.int64) if fetch else 0)
+    out = demod_digitize_distributed(ctx, rank, world, sb, global_offset, n_total, noise_mag, mod_type, float(center), tolerance,
+                                     samples_per_symbol, bits_per_symbol, center_spacing, None, fetch)
+    return center, out
+
+
 def merge_shard_rows(parts):
     """concatenate per-shard pulse tables; equal states that meet at a shard edge are one pulse (pyx:475-476)"""
     out = []
