@@ -28,7 +28,9 @@ if ROOT not in sys.path:
 
 SPS = 100
 FS = 2e6
-FDEV = 20e3
+# +-100 kHz: detect_center's peak test needs the two levels >= 5 % of the histogram span apart, and a bursty capture's span is
+# 2*pi (one random-phase sample opens every burst), so a whole-capture center needs a deviation of >= ~0.16 rad/sample
+FDEV = 100e3
 NOISE_MAG = 0.05
 SIGMA = 0.01
 TOL = 5
@@ -179,7 +181,7 @@ def main():
     world = env_int("WORLD_SIZE", 1)
     n = 1 << args.log2n
     workload = ("2-FSK complex64, ONE capture of %d x 2^%d samples sharded by contiguous range (1-sample halo, NCCL run stitching) "
-                "@2MS/s sps=100 +-20kHz AWGN sigma=0.01 bursts+gaps; %s (tol=5, noise=0.05)"
+                "@2MS/s sps=100 +-100kHz AWGN sigma=0.01 bursts+gaps; %s (tol=5, noise=0.05)"
                 % (world, args.log2n, "demod + detect_center (capture-wide) + digitize" if args.center == "detect"
                    else "fused demod+digitize, center=0 given"))
     base = {"metric": "MSamples/s IQ demod+digitize (complex64)", "unit": "MSamples/s", "n_gpus": args.gpus,
@@ -266,7 +268,7 @@ def main():
             dense_of_step[0] = read_dense_ms()
             center_seen[0] = center
             return udist.demod_digitize_distributed(ctx, rank, world, sb, offset, n_total, NOISE_MAG, "FSK", float(center), TOL, SPS,
-                                                    fetch=False)
+                                                    fetch=False, qad_source=d_qad)
         _, center = AI.demod_detect_center(d_iq, NOISE_MAG, "FSK", out=d_qad)
         dense_of_step[0] = read_dense_ms()
         center_seen[0] = center

@@ -159,6 +159,9 @@ int urh_spectrogram_db(urh_ctx* ctx, const float* d_x, int64_t n, int window_siz
 int urh_shard_dense(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int has_halo, float noise_mag, int mod_type,
                     float center, uint16_t tolerance, uint8_t bits_per_symbol, float center_spacing, float* d_qad_out,
                     int64_t* h_summary);
+/* the same step for a shard that is already demodulated (digitizing once a capture-wide center is known) */
+int urh_shard_dense_qad(urh_ctx* ctx, const float* d_qad, int64_t n, int mod_type, float center, uint16_t tolerance,
+                        uint8_t bits_per_symbol, float center_spacing, int64_t* h_summary);
 int urh_shard_candidates(urh_ctx* ctx, int carry_valid, int carry_cls, int64_t carry_len, int64_t global_offset,
                          int64_t* count, const int64_t** d_pos, const int16_t** d_cls, int* last_cand_cls);
 /* distributed finish (no gather): every rank keeps its own rows; see urh_b200/dist.py for the two scalars exchanged */

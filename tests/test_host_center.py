@@ -1,0 +1,63 @@
+"""Host half of detect_center (no GPU): vectorised peak picking == the reference's per-bin loop
+(AutoInterpretation.py:213-240), rank window and statistics bookkeeping."""
+import numpy as np
+
+from urh_b200.ainterpretation import AutoInterpretation as AI
+
+
+def loop_pick(y, edges):
+    """literal restatement of the reference loop"""
+    num_values = len(y)
+    most_common_levels = []
+    window_size = max(2, int(0.05 * num_values) + 1)
+    for index in np.argsort(y)[::-1]:
+        is_local_maximum = True
+        for i in range(1, window_size):
+            right = y[index + i] if index + i < num_values else 0
+            left = y[index - i] if index - i >= 0 else 0
+            if not (y[index] > right and y[index] > left):
+                is_local_maximum = False
+                break
+        if is_local_maximum:
+            most_common_levels.append(edges[index])
+        if len(most_common_levels) == 2:
+            break
+    if len(most_common_levels) == 0:
+        return None
+    return np.mean(most_common_levels)
+
+
+def test_peak_picking_matches_loop():
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        nbins = int(rng.integers(1, 400))
+        kind = trial % 4
+        if kind == 0:
+            y = rng.integers(0, 50, nbins)
+        elif kind == 1:
+            y = np.zeros(nbins, dtype=np.int64)
+            y[rng.integers(0, nbins, 3)] = rng.integers(1, 1000, 3)
+        elif kind == 2:
+            g = np.arange(nbins)
+            y = (1000 * np.exp(-0.5 * ((g - nbins * 0.3) / 3.0) ** 2) + 800 * np.exp(-0.5 * ((g - nbins * 0.7) / 3.0) ** 2)).astype(np.int64)
+            y += rng.integers(0, 3, nbins)
+        else:
+            y = np.full(nbins, 7, dtype=np.int64)  # plateau: no strict maximum
+        edges = np.arange(nbins + 1) * 0.01 - 1.0
+        a, b = AI.pick_center_from_histogram(y.astype(np.int64), edges), loop_pick(y.astype(np.int64), edges)
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a == b
+
+
+def test_rank_window_and_stats():
+    assert AI.center_rank_window(1000) == (50, 950)
+    assert AI.center_rank_window(1000, 100) == (50, 150)
+    assert AI.center_rank_window(10, None) == (0, 9)
+    assert AI.center_rank_window(0) == (0, 0)
+    st = AI.center_stats_from_window(100, 5, 95, np.array([90.0, -1.0, 2.0, 45.0, 100.0]))
+    assert st[3] == -1.0 and st[4] == 2.0 and st[5] == 0.5 and abs(st[6] - (100.0 - 90 * 0.25) / 90) < 1e-15
+    empty = AI.center_stats_from_window(100, 5, 95, np.zeros(5))
+    assert AI.center_bin_edges(empty) is None
+    const = AI.center_stats_from_window(100, 5, 95, np.array([90.0, 1.0, 1.0, 90.0, 90.0]))
+    assert AI.center_bin_edges(const) is None  # zero variance: arange raises -> no center

@@ -97,6 +97,7 @@ SIGNATURES = {
     "urh_stft": (i32, [vp, vp, i64, i32, i32, vp, i64, vp]),
     "urh_spectrogram_db": (i32, [vp, vp, i64, i32, i32, vp, i64, vp]),
     "urh_shard_dense": (i32, [vp, vp, i32, i64, i32, f32, i32, f32, u16, u8, f32, vp, vp]),
+    "urh_shard_dense_qad": (i32, [vp, vp, i64, i32, f32, u16, u8, f32, vp]),
     "urh_shard_candidates": (i32, [vp, i32, i32, i64, i64, C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]),
     "urh_shard_fire": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
     "urh_shard_rows": (i32, [vp, i64, u16, i32, u32, i64, i32, C.POINTER(i64)]),

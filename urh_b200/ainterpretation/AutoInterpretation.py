@@ -220,20 +220,19 @@ def pick_center_from_histogram(y, edges):
     5 % neighbourhood; center = mean of their left edges."""
     nbins = len(edges) - 1
     window = max(2, int(0.05 * nbins) + 1)
+    # same decision as the reference's loop, evaluated for every bin at once: a peak exceeds every neighbour within
+    # `window` bins on both sides (bins beyond the ends count as 0)
+    y = np.asarray(y)
+    padded = np.concatenate([np.zeros(window, dtype=y.dtype), y, np.zeros(window, dtype=y.dtype)])
+    is_peak = np.ones(nbins, dtype=bool)
+    for i in range(1, window):
+        is_peak &= (y > padded[window + i:window + i + nbins]) & (y > padded[window - i:window - i + nbins])
     levels = []
     for index in np.argsort(y)[::-1]:
-        v = y[index]
-        is_peak = True
-        for i in range(1, window):
-            right = y[index + i] if index + i < nbins else 0
-            left = y[index - i] if index - i >= 0 else 0
-            if not (v > right and v > left):
-                is_peak = False
-                break
-        if is_peak:
+        if is_peak[index]:
             levels.append(edges[index])
-        if len(levels) == 2:
-            break
+            if len(levels) == 2:
+                break
     if len(levels) == 0:
         return None
     return np.mean(levels)

@@ -32,6 +32,29 @@ k_dense_f32(const T* __restrict__ x, int64_t n, int vec_in, const __grid_constan
     const int iters = (tile_len + 63) >> 6;
     UrhRunTracker rt;
     rt.init(tol, staging + tile * (int64_t)stage_cap);
+    if (vec_in && tile_len == URH_TILE) {
+        // full tile: eight 64-groups in flight per warp (four being classified, four being loaded)
+        typedef typename UrhVec2<T>::type V;
+        const V* p = (const V*)(x + tile_start) + lane;  // 64-group `it` -> p[it * 32]
+        constexpr int ITERS = URH_TILE / 64;
+        V cur[4], nxt[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) cur[j] = __ldg(p + j * 32);
+        if (tile_start == 0 && lane == 0 && init_cls) *init_cls = (int16_t)(((float)cur[0].x == cls.noise_value) ? -1 : cls_of_zero);
+        for (int it = 0; it < ITERS; it += 4) {
+            if (it + 4 < ITERS) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) nxt[j] = __ldg(p + (it + 4 + j) * 32);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                rt.feed(it + j, SRC::template cls<T>(cur[j].x, cls), SRC::template cls<T>(cur[j].y, cls), true, true, lane);
+#pragma unroll
+            for (int j = 0; j < 4; j++) cur[j] = nxt[j];
+        }
+        rt.finish(tile_len, tiles + tile, lane);
+        return;
+    }
     // two 64-groups in flight per warp step
     for (int it = 0; it < iters; it += 2) {
         T a0 = 0, a1 = 0, b0 = 0, b1 = 0;

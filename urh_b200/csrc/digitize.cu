@@ -415,6 +415,42 @@ extern "C" int urh_shard_dense(urh_ctx* ctx, const void* d_iq, int dtype, int64_
     return URH_OK;
 }
 
+// Step 1 for a shard that is already demodulated (the center became known only after the demodulation pass): the
+// digitizer's dense pass over qad.  Classification is per sample, so no halo is involved; same h_summary as urh_shard_dense.
+extern "C" int urh_shard_dense_qad(urh_ctx* ctx, const float* d_qad, int64_t n, int mod_type, float center, uint16_t tolerance,
+                                   uint8_t bits_per_symbol, float center_spacing, int64_t* h_summary) {
+    if (n <= 0) URH_FAIL(ctx, URH_ERR_INVALID, "empty shard");
+    urh_arena_reset(ctx);
+    UrhClassify cls;
+    URH_CHECK(fill_classify(ctx, &cls, mod_type, center, bits_per_symbol, center_spacing));
+    const int tol = tolerance;
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    const int cap = stage_cap_for(tol);
+    UrhTileSummary* tiles;
+    uint32_t* staging;
+    int16_t* d_init;
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles, &tiles));
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles * cap, &staging));
+    URH_CHECK(urh_arena(ctx, 8, &d_init));
+    URH_CUDA(ctx, cudaMemsetAsync(d_init, 0, 16, ctx->stream));
+    const int vec_in = (((uintptr_t)d_qad % 8) == 0) ? 1 : 0;
+    URH_PROF_BEGIN(ctx);
+    URH_LAUNCH(ctx, (k_dense_f32<SrcQad, float>), (unsigned)urh_div_up(ntiles, URH_WARPS_PER_BLOCK), URH_WARPS_PER_BLOCK * 32, 0, d_qad, n,
+               vec_in, cls, tol, tiles, staging, cap, d_init, host_classify(0.0f, cls));
+    URH_PROF_END(ctx);
+    ctx->shard_tiles = tiles;
+    ctx->shard_staging = staging;
+    ctx->shard_cap = cap;
+    ctx->shard_n = n;
+    ctx->shard_tol = tol;
+    URH_CHECK(urh_shard_run_total(ctx, n, tiles, h_summary));
+    int16_t init16 = 0;
+    URH_CUDA(ctx, cudaMemcpyAsync(&init16, d_init, sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    h_summary[3] = init16;
+    return URH_OK;
+}
+
 struct UrhShardState {
     UrhCandidates cand;
     UrhFireState fs;

@@ -649,42 +649,65 @@ __global__ void __launch_bounds__(256) k_interior_tile_stats(const UrhTileStats*
     }
 }
 
-// histogram over the dense pass's tiles: interior tiles need no rank bookkeeping
+// histogram over the dense pass's tiles: interior tiles need no rank bookkeeping.  A demodulated capture piles its
+// samples onto a handful of bins, so lanes that hit the same bin are merged (__match_any_sync) into one shared-memory atomic.
 __global__ void __launch_bounds__(256) k_hist_tiles(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ prefix,
                                                    int64_t ntiles, int64_t r0, int64_t r1, double hmin, double hstep, int64_t nbins,
                                                    unsigned long long* __restrict__ hist, int hist_in_smem) {
     extern __shared__ unsigned int s_hist[];
     __shared__ int s_pre[256];
+    const int lane = threadIdx.x & 31;
     if (hist_in_smem) {
         for (int64_t b = threadIdx.x; b < nbins; b += 256) s_hist[b] = 0u;
         __syncthreads();
     }
     const double last_edge = hmin + (double)nbins * hstep;
     const double inv = 1.0 / hstep;
-    auto put = [&](float f) {
+    // bin of one value, -1 when it does not count (np.histogram: half-open bins, the last one closed)
+    auto bin_of = [&](float f, bool counts) -> int {
+        if (!counts) return -1;
         const double a = (double)f;
+        if (!(a >= hmin && a <= last_edge)) return -1;
         int64_t k = (int64_t)floor((a - hmin) * inv);
         if (k < 0) k = 0;
         if (k > nbins - 1) k = nbins - 1;
         while (k > 0 && a < hmin + (double)k * hstep) k--;
         while (k < nbins - 1 && a >= hmin + (double)(k + 1) * hstep) k++;
-        if (a >= hmin && a <= last_edge) {
-            if (hist_in_smem) atomicAdd(&s_hist[k], 1u);
-            else atomicAdd(&hist[k], 1ull);
+        return (int)k;
+    };
+    // called by all 32 lanes of a warp together
+    auto put = [&](int k) {
+        const unsigned peers = __match_any_sync(URH_FULL_MASK, k);
+        if (k >= 0 && lane == __ffs(peers) - 1) {
+            if (hist_in_smem) atomicAdd(&s_hist[k], (unsigned)__popc(peers));
+            else atomicAdd(&hist[k], (unsigned long long)__popc(peers));
         }
     };
     const int per = URH_TILE / 256;
+    const bool vec = (((uintptr_t)x) & 15) == 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t a = prefix[t], b = prefix[t + 1];
         if (b <= a || b <= r0 || a >= r1) continue;  // block-uniform
         const int64_t base = t * URH_TILE;
         if (a >= r0 && b <= r1) {
             // interior: coalesced, every kept sample counts
-            for (int j = threadIdx.x; j < URH_TILE; j += 256) {
-                const int64_t i = base + j;
-                if (i < n) {
-                    const float f = x[i];
-                    if (f > -4.0f) put(f);
+            if (vec && base + URH_TILE <= n) {
+                const float4* p4 = (const float4*)(x + base);
+                float4 v[URH_TILE / 1024];
+#pragma unroll
+                for (int j = 0; j < URH_TILE / 1024; j++) v[j] = __ldg(p4 + j * 256 + threadIdx.x);
+#pragma unroll
+                for (int j = 0; j < URH_TILE / 1024; j++) {
+                    put(bin_of(v[j].x, v[j].x > -4.0f));
+                    put(bin_of(v[j].y, v[j].y > -4.0f));
+                    put(bin_of(v[j].z, v[j].z > -4.0f));
+                    put(bin_of(v[j].w, v[j].w > -4.0f));
+                }
+            } else {
+                for (int j = threadIdx.x; j < URH_TILE; j += 256) {
+                    const int64_t i = base + j;
+                    const float f = (i < n) ? x[i] : -5.0f;
+                    put(bin_of(f, f > -4.0f));
                 }
             }
         } else {
@@ -708,10 +731,9 @@ __global__ void __launch_bounds__(256) k_hist_tiles(const float* __restrict__ x,
             int64_t rank = a + s_pre[threadIdx.x] - mine;
 #pragma unroll
             for (int j = 0; j < per; j++) {
-                if (v[j] > -4.0f) {
-                    if (rank >= r0 && rank < r1) put(v[j]);
-                    rank++;
-                }
+                const bool kept = v[j] > -4.0f;
+                put(bin_of(v[j], kept && rank >= r0 && rank < r1));
+                rank += kept ? 1 : 0;
             }
             __syncthreads();
         }
@@ -721,6 +743,18 @@ __global__ void __launch_bounds__(256) k_hist_tiles(const float* __restrict__ x,
         for (int64_t b = threadIdx.x; b < nbins; b += 256)
             if (s_hist[b]) atomicAdd(&hist[b], (unsigned long long)s_hist[b]);
     }
+}
+
+// the (at most two) tiles the rank window [r0, r1) cuts: tile t holds ranks [prefix[t], prefix[t+1]).  edges[q] = tile index
+// or -1 (no such tile / the window covers it completely, so the interior kernel takes it / same tile as edges[0]).
+__global__ void k_find_edge_tiles(const int64_t* __restrict__ prefix, int64_t ntiles, int64_t r0, int64_t r1, int64_t* __restrict__ edges) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const int64_t a = prefix[t], b = prefix[t + 1];
+    if (b <= a) return;
+    const bool covered = a >= r0 && b <= r1;
+    if (a <= r0 && r0 < b) edges[0] = covered ? -1 : t;
+    if (a <= r1 - 1 && r1 - 1 < b && !(a <= r0 && r0 < b)) edges[1] = covered ? -1 : t;
 }
 
 // Rank prefix over the tile table the demodulator produced; leaves {ts, prefix, n} in ctx for the window / histogram calls.
@@ -755,31 +789,9 @@ extern "C" int urh_center_window_stats(urh_ctx* ctx, const float* d_qad, int64_t
     URH_CHECK(urh_arena(ctx, 4, &d_edges));
     URH_CHECK(urh_arena(ctx, (size_t)nb + 4, &partial));
     URH_CHECK(urh_arena(ctx, 2, &folded));
-    // the (at most two) tiles cut by the window: found on the host by bisection over the prefix (tiny read-backs)
-    auto tile_of_rank = [&](int64_t r, int64_t* out_t) -> int {
-        int64_t lo = 0, hi = ntiles;  // largest t with prefix[t] <= r
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) / 2;
-            int64_t v;
-            URH_CHECK(urh_read_i64(ctx, prefix + mid, 1, &v));
-            if (v <= r) lo = mid; else hi = mid;
-        }
-        *out_t = lo;
-        return URH_OK;
-    };
-    int64_t e[2] = {-1, -1};
-    URH_CHECK(tile_of_rank(r0, &e[0]));
-    URH_CHECK(tile_of_rank(r1 - 1, &e[1]));
-    if (e[1] == e[0]) e[1] = -1;
-    // a cut tile is "edge" unless the window covers it completely (then the interior kernel takes it)
-    for (int q = 0; q < 2; q++) {
-        if (e[q] < 0) continue;
-        int64_t ab[2];
-        URH_CHECK(urh_read_i64(ctx, prefix + e[q], 2, ab));
-        if (ab[0] >= r0 && ab[1] <= r1) e[q] = -1;
-    }
-    URH_CUDA(ctx, cudaMemcpyAsync(d_edges, e, sizeof(e), cudaMemcpyHostToDevice, ctx->stream));
-    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t none[2] = {-1, -1};
+    URH_CUDA(ctx, cudaMemcpyAsync(d_edges, none, sizeof(none), cudaMemcpyHostToDevice, ctx->stream));
+    URH_LAUNCH(ctx, k_find_edge_tiles, (unsigned)urh_div_up(ntiles, 256), 256, 0, prefix, ntiles, r0, r1, d_edges);
     URH_LAUNCH(ctx, k_interior_tile_stats, nb, 256, 0, ts, prefix, ntiles, r0, r1, partial);
     URH_LAUNCH(ctx, k_edge_tile_stats, 2, 256, 0, d_qad, n, prefix, d_edges, r0, r1, partial + nb);
     URH_LAUNCH(ctx, k_center_fold, 1, 256, 0, partial, (int64_t)nb + 2, folded);

@@ -199,18 +199,23 @@ def previous_nonempty(values, counts, rank, default):
 
 
 def demod_digitize_distributed(ctx, rank, world, sb: ShardBuffer, global_offset, n_total, noise_mag, mod_type, center, tolerance,
-                               samples_per_symbol, bits_per_symbol=1, center_spacing=0.1, d_qad=None, fetch=True):
+                               samples_per_symbol, bits_per_symbol=1, center_spacing=0.1, d_qad=None, fetch=True, qad_source=None):
     """Sharded FSK/ASK demod + digitize with a DISTRIBUTED finish: no gather, every rank ends with the rows of its own
     shard (``merge_shard_rows`` joins them).  Three NCCL all-gathers of a few int64 per rank are the whole exchange:
       (last_cls, last_len, whole, init_cls)  ->  run carry into the shard;
       (candidate count, class of the last candidate)  ->  fire decision of the shard's first candidate;
-      (firing count, position of the last firing)  ->  length of the shard's first pulse."""
+      (firing count, position of the last firing)  ->  length of the shard's first pulse.
+    ``qad_source``: the shard is already demodulated (float32 DeviceArray) -> digitize from it instead of the IQ samples."""
     lib = ctx.lib
     code = _lib.demod_mod_code(mod_type)
     summary = (C.c_int64 * 4)()
-    ctx.check(lib.urh_shard_dense(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, int(rank > 0),
-                                  float(noise_mag), code, float(center), int(tolerance), int(bits_per_symbol), float(center_spacing),
-                                  C.c_void_p(d_qad.ptr if d_qad is not None else 0), summary))
+    if qad_source is not None:
+        ctx.check(lib.urh_shard_dense_qad(ctx.handle, C.c_void_p(qad_source.ptr), sb.n, code, float(center), int(tolerance),
+                                          int(bits_per_symbol), float(center_spacing), summary))
+    else:
+            ctx.check(lib.urh_shard_dense(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, int(rank > 0),
+                                      float(noise_mag), code, float(center), int(tolerance), int(bits_per_symbol), float(center_spacing),
+                                      C.c_void_p(d_qad.ptr if d_qad is not None else 0), summary))
     every = nccl_allgather_i64(ctx, world, list(summary))
     carry = fold_carry([(int(c), int(l), int(w)) for c, l, w, _ in every])[rank]
     init_cls = int(every[0][3])
@@ -275,12 +280,12 @@ def detect_center_distributed(ctx, rank, world, sb: ShardBuffer, noise_mag, mod_
 def demod_center_digitize_distributed(ctx, rank, world, sb: ShardBuffer, global_offset, n_total, noise_mag, mod_type, tolerance,
                                       samples_per_symbol, d_qad, bits_per_symbol=1, center_spacing=0.1, max_size=None, fetch=True):
     """BASELINE configs[1]/[4] on N GPUs: demod + capture-wide detect_center + digitize of ONE sharded capture.
-    The digitizer pass re-reads the shard's IQ (urh_shard_dense) once the center is known.  -> (center, rows or count)."""
+    The digitizer pass reads the shard's qad (4 B/sample) once the center is known.  -> (center, rows or count)."""
     center = detect_center_distributed(ctx, rank, world, sb, noise_mag, mod_type, d_qad, max_size)
     if center is None:
         return None, (np.zeros((0, 2), dtype=np.int64) if fetch else 0)
     out = demod_digitize_distributed(ctx, rank, world, sb, global_offset, n_total, noise_mag, mod_type, float(center), tolerance,
-                                     samples_per_symbol, bits_per_symbol, center_spacing, None, fetch)
+                                     samples_per_symbol, bits_per_symbol, center_spacing, None, fetch, qad_source=d_qad)
     return center, out
 
 
