@@ -148,3 +148,44 @@ def test_demod_center_digitize_matches_three_calls(AI):
     c2 = center
     assert np.array_equal(rows, sf.grab_pulse_lens(qad, c2, 5, "FSK", 100))
     assert rows[:, 1].sum() == len(iq) - 5
+
+
+@pytest.mark.parametrize("nbins_target", [7, 64, 1500, 7000, 20000])
+def test_tile_histogram_counts_equal_numpy(AI, nbins_target):
+    """urh_center_histogram_tiles (float edge thresholds, register-counted hot bins) == np.histogram on the same edges."""
+    import ctypes as C
+    from urh_b200 import _lib
+    from urh_b200.device import DeviceArray, to_device
+    n = 300_001
+    iq = synth_fsk(n, seed=nbins_target, gap_every=50_000)
+    ctx = _lib.default_context()
+    d_iq = to_device(iq, ctx)
+    qad = DeviceArray(ctx, (n,), np.float32)
+    kept = C.c_int64(0)
+    ctx.check(ctx.lib.urh_afp_demod_tiles(ctx.handle, C.c_void_p(d_iq.ptr), _lib.dtype_code(d_iq.dtype), n, 0.05, _lib.MOD_FSK,
+                                          C.c_void_p(qad.ptr), 0, C.byref(kept)))
+    host = qad.get()
+    rect_all = host[host > -4]
+    assert kept.value == len(rect_all)
+    r0, r1 = AI.center_rank_window(kept.value)
+    rect = rect_all[r0:r1]
+    w = np.zeros(5)
+    ctx.check(ctx.lib.urh_center_window_stats(ctx.handle, C.c_void_p(qad.ptr), n, r0, r1, w.ctypes.data_as(C.c_void_p)))
+    assert int(w[0]) == len(rect) and np.float32(w[1]) == rect.min() and np.float32(w[2]) == rect.max()
+    assert abs(w[3] - rect.astype(np.float64).sum()) <= 1e-9 * len(rect)
+    # edges that cut through the data: interior start/stop so that out-of-range samples exist on both sides
+    lo, hi = float(np.percentile(rect, 1)), float(np.percentile(rect, 99.5))
+    step = (hi - lo) / nbins_target
+    edges = np.arange(lo, hi + step, step)
+    nbins = len(edges) - 1
+    y = np.zeros(nbins, dtype=np.int64)
+    ctx.check(ctx.lib.urh_center_histogram_tiles(ctx.handle, C.c_void_p(qad.ptr), n, r0, r1, C.c_double(edges[0]),
+                                                 C.c_double(edges[1] - edges[0]), nbins, y.ctypes.data_as(C.c_void_p)))
+    # np.arange fills start + i*delta: rebuild exactly those edges for numpy
+    exact_edges = edges[0] + np.arange(nbins + 1) * (edges[1] - edges[0])
+    ref, _ = np.histogram(rect, bins=exact_edges)
+    assert np.array_equal(y, ref)
+    y2 = np.zeros(nbins, dtype=np.int64)
+    ctx.check(ctx.lib.urh_center_histogram(ctx.handle, C.c_void_p(qad.ptr), n, r0, r1, C.c_double(edges[0]),
+                                           C.c_double(edges[1] - edges[0]), nbins, y2.ctypes.data_as(C.c_void_p)))
+    assert np.array_equal(y2, ref)

@@ -55,6 +55,7 @@ struct urh_ctx {
     // NCCL (nccl.cu)
     int64_t costas_stats[3];
     const void* center_ts;
+    const void* center_x;
     int64_t center_n;
     void* center_prefix;  // tile rank prefix left by urh_afp_demod_stats for urh_center_histogram_tiles (arena)
     void* nccl_comm;

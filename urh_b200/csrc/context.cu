@@ -31,6 +31,9 @@ extern "C" int urh_ctx_create(int device, urh_ctx** out) {
     ctx->shard_staging = nullptr;
     ctx->shard_state = nullptr;
     ctx->center_prefix = nullptr;
+    ctx->center_ts = nullptr;
+    ctx->center_x = nullptr;
+    ctx->center_n = 0;
     ctx->nccl_comm = nullptr;
     ctx->nccl_stage = nullptr;
     ctx->nccl_rank = 0;
@@ -213,6 +216,7 @@ void urh_arena_reset(urh_ctx* ctx) {
     ctx->arena_block = 0;
     ctx->arena_used = 0;
     ctx->arena_need = 0;
+    ctx->center_prefix = nullptr;  // the detect_center tile table lived in the arena
 }
 
 int urh_arena_alloc(urh_ctx* ctx, size_t bytes, void** out) {

@@ -260,7 +260,7 @@ extern "C" int urh_afp_demod(urh_ctx* ctx, const void* d_iq, int dtype, int64_t 
     return launch_dense_iq_m<URH_MOD_FSK, false>(ctx, dtype, d_iq, n, dp, d_out, cls, 0, nullptr, nullptr, 0, nullptr, 0);
 }
 
-int urh_center_tiles_begin(urh_ctx* ctx, const UrhTileStats* ts, int64_t n, int64_t* h_total);  // stats.cu
+int urh_center_tiles_begin(urh_ctx* ctx, const float* d_x, const UrhTileStats* ts, int64_t n, int64_t* h_total);  // center.cu
 
 // afp_demod (ASK / FSK) that also collects, in the same pass over the IQ samples, what detect_center needs: per-tile
 // {count, min, max, sum, sumsq} of the samples it keeps (> -4).  *h_kept = number of kept samples.  The table stays in
@@ -273,7 +273,6 @@ extern "C" int urh_afp_demod_tiles(urh_ctx* ctx, const void* d_iq, int dtype, in
         URH_FAIL(ctx, URH_ERR_INVALID, "urh_afp_demod_tiles: ASK/FSK, n > 2 and a qad buffer are required");
     if (urh_iq_bytes(dtype) == 0) URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
     urh_arena_reset(ctx);
-    ctx->center_prefix = nullptr;
     const UrhDemodParams dp = make_demod_params(noise_mag, mod_type, dtype);
     UrhClassify cls;
     memset(&cls, 0, sizeof(cls));
@@ -284,7 +283,7 @@ extern "C" int urh_afp_demod_tiles(urh_ctx* ctx, const void* d_iq, int dtype, in
         URH_CHECK((launch_dense_iq_m<URH_MOD_ASK, false>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, 0, nullptr, nullptr, 0, nullptr, 0, halo, ts)));
     else
         URH_CHECK((launch_dense_iq_m<URH_MOD_FSK, false>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, 0, nullptr, nullptr, 0, nullptr, 0, halo, ts)));
-    return urh_center_tiles_begin(ctx, ts, n, h_kept);
+    return urh_center_tiles_begin(ctx, d_qad_out, ts, n, h_kept);
 }
 
 // Shared tail of the two digitizer entry points: tile table + staging -> merged (state, length) rows.

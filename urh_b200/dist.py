@@ -213,9 +213,9 @@ def demod_digitize_distributed(ctx, rank, world, sb: ShardBuffer, global_offset,
         ctx.check(lib.urh_shard_dense_qad(ctx.handle, C.c_void_p(qad_source.ptr), sb.n, code, float(center), int(tolerance),
                                           int(bits_per_symbol), float(center_spacing), summary))
     else:
-            ctx.check(lib.urh_shard_dense(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, int(rank > 0),
-                                      float(noise_mag), code, float(center), int(tolerance), int(bits_per_symbol), float(center_spacing),
-                                      C.c_void_p(d_qad.ptr if d_qad is not None else 0), summary))
+        ctx.check(lib.urh_shard_dense(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, int(rank > 0),
+                                      float(noise_mag), code, float(center), int(tolerance), int(bits_per_symbol),
+                                      float(center_spacing), C.c_void_p(d_qad.ptr if d_qad is not None else 0), summary))
     every = nccl_allgather_i64(ctx, world, list(summary))
     carry = fold_carry([(int(c), int(l), int(w)) for c, l, w, _ in every])[rank]
     init_cls = int(every[0][3])
