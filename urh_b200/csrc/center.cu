@@ -262,22 +262,44 @@ extern "C" int urh_center_stats(urh_ctx* ctx, const float* d_x, int64_t n, int64
 // ---- 3. histogram -------------------------------------------------------------------------------------------------------
 // Bin edges of np.histogram as FLOAT thresholds: a float sample f satisfies f >= edge_k (double) iff f >= ru(edge_k), the
 // smallest float not below the edge, so the binning needs no double arithmetic and stays exact.
-// fe[0..nbins] = ru(hmin + k*hstep); fe[nbins+1] = rd(last edge) (np.histogram closes the last bin).
+// fe[0..nbins] = ru(hmin + k*hstep); fe[nbins+1] = rd(last edge) (np.histogram closes the last bin);
+// fe[nbins+2] = the smallest float that both exceeds -4 (detect_center's filter) and reaches the first edge.
 __global__ void k_hist_edges(double hmin, double hstep, int64_t nbins, float* __restrict__ fe) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // edges exactly as np.arange forms them: one rounded product, one rounded sum (no FMA)
     if (k <= nbins) fe[k] = __double2float_ru(__dadd_rn(hmin, __dmul_rn((double)k, hstep)));
-    if (k == nbins) fe[nbins + 1] = __double2float_rd(__dadd_rn(hmin, __dmul_rn((double)nbins, hstep)));
+    if (k == nbins) {
+        fe[nbins + 1] = __double2float_rd(__dadd_rn(hmin, __dmul_rn((double)nbins, hstep)));
+        fe[nbins + 2] = fmaxf(__double2float_ru(hmin), nextafterf(-4.0f, 0.0f));
+    }
 }
 
+// FAST: the bin guess rn((f - hmin) / hstep) in float arithmetic is off by less than half a bin (the host checks
+// |edge| / hstep < 2^20), so the true bin is the guess or the one below it: one table look-up, no loop.
 struct HistBins {
     const float* fe;   // thresholds (shared or global)
-    float f_lo, f_hi, scale;
+    float f_min, f_hi, scale, off;
     int nbins;
+    __device__ __forceinline__ void load(const float* fe_, float scale_, int nbins_) {
+        fe = fe_; nbins = nbins_; scale = scale_;
+        f_hi = fe[nbins + 1];
+        f_min = fe[nbins + 2];
+        off = -fe[0] * scale;
+    }
     // bin of one value, -1 when it does not count (np.histogram: half-open bins, the last one closed)
-    __device__ __forceinline__ int bin_of(float f, bool counts) const {
-        if (!(counts && f >= f_lo && f <= f_hi)) return -1;
-        int k = (int)((f - f_lo) * scale);
+    template <bool FAST>
+    __device__ __forceinline__ int bin_of(float f) const {
+        const bool valid = f >= f_min && f <= f_hi;
+        if (FAST) {
+            const float t = fmaf(f, scale, off);
+            int r = __float_as_int(t + 12582912.0f) - 0x4B400000;   // round to nearest via the 1.5 * 2^23 trick
+            r = max(0, min(r, nbins));
+            int k = r - ((f < fe[r]) ? 1 : 0);
+            k = min(k, nbins - 1);
+            return valid ? k : -1;
+        }
+        if (!valid) return -1;
+        int k = (int)((f - fe[0]) * scale);
         k = max(0, min(k, nbins - 1));
         while (k > 0 && f < fe[k]) k--;
         while (k < nbins - 1 && f >= fe[k + 1]) k++;
@@ -286,7 +308,7 @@ struct HistBins {
 };
 
 // A demodulated capture piles its samples onto a handful of bins.  Each thread keeps four (bin, count) pairs in registers;
-// a sample whose bin is not among them goes to the histogram directly and takes over the least used pair.
+// a sample whose bin is not among them takes over the least used pair (whose count goes to the histogram).
 struct HistCache {
     int h0, h1, h2, h3;
     unsigned c0, c1, c2, c3;
@@ -300,25 +322,33 @@ __device__ __forceinline__ void hist_bump(unsigned int* s_hist, unsigned long lo
 }
 
 template <bool SMEM>
+__device__ __forceinline__ void hist_miss(HistCache& hc, unsigned int* s_hist, unsigned long long* hist, int k) {
+    unsigned cm = hc.c0; int which = 0;
+    if (hc.c1 < cm) { cm = hc.c1; which = 1; }
+    if (hc.c2 < cm) { cm = hc.c2; which = 2; }
+    if (hc.c3 < cm) { cm = hc.c3; which = 3; }
+    const int old = which == 0 ? hc.h0 : which == 1 ? hc.h1 : which == 2 ? hc.h2 : hc.h3;
+    if (cm) hist_bump<SMEM>(s_hist, hist, old, cm);
+    if (which == 0) { hc.h0 = k; hc.c0 = 1u; }
+    else if (which == 1) { hc.h1 = k; hc.c1 = 1u; }
+    else if (which == 2) { hc.h2 = k; hc.c2 = 1u; }
+    else { hc.h3 = k; hc.c3 = 1u; }
+}
+
+template <bool SMEM>
 __device__ __forceinline__ void hist_put(HistCache& hc, unsigned int* s_hist, unsigned long long* hist, int k) {
-    const bool e0 = k == hc.h0, e1 = k == hc.h1, e2 = k == hc.h2, e3 = k == hc.h3;
-    hc.c0 += e0 ? 1u : 0u;
-    hc.c1 += e1 ? 1u : 0u;
-    hc.c2 += e2 ? 1u : 0u;
-    hc.c3 += e3 ? 1u : 0u;
-    if (k >= 0 && !(e0 | e1 | e2 | e3)) {
-        // miss: evict the pair with the smallest count, start counting this bin (this sample included)
-        unsigned cm = hc.c0; int which = 0;
-        if (hc.c1 < cm) { cm = hc.c1; which = 1; }
-        if (hc.c2 < cm) { cm = hc.c2; which = 2; }
-        if (hc.c3 < cm) { cm = hc.c3; which = 3; }
-        const int old = which == 0 ? hc.h0 : which == 1 ? hc.h1 : which == 2 ? hc.h2 : hc.h3;
-        if (cm) hist_bump<SMEM>(s_hist, hist, old, cm);
-        if (which == 0) { hc.h0 = k; hc.c0 = 1u; }
-        else if (which == 1) { hc.h1 = k; hc.c1 = 1u; }
-        else if (which == 2) { hc.h2 = k; hc.c2 = 1u; }
-        else { hc.h3 = k; hc.c3 = 1u; }
-    }
+    // four compare + predicated-increment pairs (spelled out: the compiler otherwise materialises count+1 and selects)
+    unsigned miss;
+    asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+        "setp.eq.s32 p0, %5, %6;\n\t@p0 add.u32 %0, %0, 1;\n\t"
+        "setp.eq.s32 p1, %5, %7;\n\t@p1 add.u32 %1, %1, 1;\n\t"
+        "setp.eq.s32 p2, %5, %8;\n\t@p2 add.u32 %2, %2, 1;\n\t"
+        "setp.eq.s32 p3, %5, %9;\n\t@p3 add.u32 %3, %3, 1;\n\t"
+        "or.pred p0, p0, p1;\n\tor.pred p2, p2, p3;\n\tor.pred p0, p0, p2;\n\t"
+        "selp.u32 %4, 0, 1, p0;\n\t}"
+        : "+r"(hc.c0), "+r"(hc.c1), "+r"(hc.c2), "+r"(hc.c3), "=r"(miss)
+        : "r"(k), "r"(hc.h0), "r"(hc.h1), "r"(hc.h2), "r"(hc.h3));
+    if (miss && k >= 0) hist_miss<SMEM>(hc, s_hist, hist, k);
 }
 
 template <bool SMEM>
@@ -331,28 +361,28 @@ __device__ __forceinline__ void hist_flush(HistCache& hc, unsigned int* s_hist, 
 
 // Tiles strictly between win[0] and win[1] lie entirely inside the rank window: every kept sample counts, no rank
 // bookkeeping, no prefix reads.  One warp per tile, grid-stride, eight 512-byte rows in flight per warp.
-template <bool SMEM>
+template <bool SMEM, bool FAST>
 __global__ void __launch_bounds__(256) k_hist_interior(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ win,
                                                       const float* __restrict__ g_fe, float scale, int nbins,
                                                       unsigned long long* __restrict__ hist, int edges_in_smem) {
     extern __shared__ unsigned int s_dyn[];
     unsigned int* s_hist = s_dyn;                               // [nbins] when SMEM
-    float* s_fe = (float*)(s_dyn + (SMEM ? nbins : 0));         // [nbins + 2] when edges_in_smem
+    float* s_fe = (float*)(s_dyn + (SMEM ? nbins : 0));         // [nbins + 3] when edges_in_smem
     const int lane = threadIdx.x & 31;
     if (SMEM)
         for (int b = threadIdx.x; b < nbins; b += 256) s_hist[b] = 0u;
     if (edges_in_smem)
-        for (int b = threadIdx.x; b < nbins + 2; b += 256) s_fe[b] = g_fe[b];
+        for (int b = threadIdx.x; b < nbins + 3; b += 256) s_fe[b] = g_fe[b];
     __syncthreads();
     HistBins hb;
-    hb.fe = edges_in_smem ? s_fe : g_fe;
-    hb.f_lo = hb.fe[0]; hb.f_hi = hb.fe[nbins + 1]; hb.scale = scale; hb.nbins = nbins;
+    if (FAST) hb.load(s_fe, scale, nbins);   // FAST is only launched with the table in shared memory (LDS, not generic LD)
+    else hb.load(edges_in_smem ? s_fe : g_fe, scale, nbins);
     HistCache hc;
     hc.init();
-    const int64_t t_first = win[0] + 1, t_end = win[1];   // win[0] < 0 (empty window) -> t_end < 0: no work
+    const int64_t t_first = win[0] + 1, t_end = win[1];
     const int64_t gw = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * 8;
     const bool vec = (((uintptr_t)x) & 15) == 0;
-    if (win[0] >= 0) {
+    if (win[0] >= 0) {   // < 0: empty window
         for (int64_t t = t_first + gw; t < t_end; t += nw) {
             const int64_t base = t * URH_TILE;   // interior tiles are full tiles (t < last tile)
             if (vec) {
@@ -368,19 +398,16 @@ __global__ void __launch_bounds__(256) k_hist_interior(const float* __restrict__
                     }
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        hist_put<SMEM>(hc, s_hist, hist, hb.bin_of(cur[j].x, cur[j].x > -4.0f));
-                        hist_put<SMEM>(hc, s_hist, hist, hb.bin_of(cur[j].y, cur[j].y > -4.0f));
-                        hist_put<SMEM>(hc, s_hist, hist, hb.bin_of(cur[j].z, cur[j].z > -4.0f));
-                        hist_put<SMEM>(hc, s_hist, hist, hb.bin_of(cur[j].w, cur[j].w > -4.0f));
+                        hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(cur[j].x));
+                        hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(cur[j].y));
+                        hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(cur[j].z));
+                        hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(cur[j].w));
                     }
 #pragma unroll
                     for (int j = 0; j < 4; j++) cur[j] = nxt[j];
                 }
             } else {
-                for (int j = lane; j < URH_TILE; j += 32) {
-                    const float f = x[base + j];
-                    hist_put<SMEM>(hc, s_hist, hist, hb.bin_of(f, f > -4.0f));
-                }
+                for (int j = lane; j < URH_TILE; j += 32) hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(x[base + j]));
             }
         }
     }
@@ -401,14 +428,14 @@ __global__ void __launch_bounds__(256) k_hist_window_ends(const float* __restric
     const int64_t t = win[blockIdx.x];
     if (t < 0 || (blockIdx.x == 1 && t == win[0])) return;
     HistBins hb;
-    hb.fe = g_fe; hb.f_lo = g_fe[0]; hb.f_hi = g_fe[nbins + 1]; hb.scale = scale; hb.nbins = nbins;
+    hb.load(g_fe, scale, nbins);
     float v[CEN_PER];
     int64_t rank = cen_tile_ranks(x, n, t, prefix[t], v, s_pre);
 #pragma unroll
     for (int j = 0; j < CEN_PER; j++) {
         const bool kept = v[j] > -4.0f;
-        const int k = hb.bin_of(v[j], kept && rank >= r0 && rank < r1);
-        if (k >= 0) atomicAdd(&hist[k], 1ull);
+        const int k = hb.bin_of<false>(v[j]);
+        if (k >= 0 && rank >= r0 && rank < r1) atomicAdd(&hist[k], 1ull);
         rank += kept ? 1 : 0;
     }
 }
@@ -426,7 +453,7 @@ extern "C" int urh_center_histogram_tiles(urh_ctx* ctx, const float* d_qad, int6
     float* fe;
     int64_t* d_win;
     URH_CHECK(urh_arena(ctx, (size_t)nbins, &hist));
-    URH_CHECK(urh_arena(ctx, (size_t)nbins + 2, &fe));
+    URH_CHECK(urh_arena(ctx, (size_t)nbins + 3, &fe));
     URH_CHECK(urh_arena(ctx, 4, &d_win));
     URH_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nbins * sizeof(unsigned long long), ctx->stream));
     URH_CUDA(ctx, cudaMemsetAsync(d_win, 0xff, 4 * sizeof(int64_t), ctx->stream));
@@ -436,13 +463,17 @@ extern "C" int urh_center_histogram_tiles(urh_ctx* ctx, const float* d_qad, int6
         // shared memory (48 KB without opt-in): histogram first, then the edge table if it still fits
         const bool in_smem = nbins <= 12000;
         const int edges_smem = (in_smem && nbins <= 6000) ? 1 : 0;
-        const size_t dyn = (in_smem ? (size_t)nbins * 4 : 0) + (edges_smem ? (size_t)(nbins + 2) * 4 : 0);
+        const size_t dyn = (in_smem ? (size_t)nbins * 4 : 0) + (edges_smem ? (size_t)(nbins + 3) * 4 : 0);
         const float scale = (float)(1.0 / hstep);
+        // one-look-up binning needs the float guess to be good to half a bin
+        const double edge_abs = fmax(fabs(hmin), fabs(hmin + (double)nbins * hstep));
+        const bool fast = edges_smem && hstep > 0.0 && edge_abs / hstep < 1048576.0;
         const unsigned gs = (unsigned)min(urh_div_up(ntiles, 8), (int64_t)ctx->sm_count * 8);
-        if (in_smem)
-            URH_LAUNCH(ctx, k_hist_interior<true>, gs, 256, dyn, d_qad, n, (const int64_t*)d_win, (const float*)fe, scale, (int)nbins, hist, edges_smem);
-        else
-            URH_LAUNCH(ctx, k_hist_interior<false>, gs, 256, dyn, d_qad, n, (const int64_t*)d_win, (const float*)fe, scale, (int)nbins, hist, edges_smem);
+        const int64_t* cw = d_win;
+        const float* cfe = fe;
+        if (in_smem && fast) URH_LAUNCH(ctx, (k_hist_interior<true, true>), gs, 256, dyn, d_qad, n, cw, cfe, scale, (int)nbins, hist, edges_smem);
+        else if (in_smem) URH_LAUNCH(ctx, (k_hist_interior<true, false>), gs, 256, dyn, d_qad, n, cw, cfe, scale, (int)nbins, hist, edges_smem);
+        else URH_LAUNCH(ctx, (k_hist_interior<false, false>), gs, 256, dyn, d_qad, n, cw, cfe, scale, (int)nbins, hist, edges_smem);
         URH_LAUNCH(ctx, k_hist_window_ends, 2, 256, 0, d_qad, n, prefix, (const int64_t*)d_win, r0, r1, (const float*)fe, scale, (int)nbins, hist);
     }
     URH_CUDA(ctx, cudaMemcpyAsync(h_hist, hist, (size_t)nbins * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
