@@ -35,6 +35,10 @@ NOISE_MAG = 0.05
 SIGMA = 0.01
 TOL = 5
 CENTER = 0.0
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per sample, from the ncu --set full captures in profiles/
+# (taken at 2^28 samples; the kernels stream, so DRAM bytes scale with n)
+TRAFFIC_B_PER_SAMPLE = {"detect": (2.147530e9 + 1.026364e9) / (1 << 28), "given": None}
+TRAFFIC_SOURCE = "profiles/r01_ncu_detect_m_summary.txt (ncu --set full at 2^28 samples, scaled by n)"
 ALG_BYTES_PER_SAMPLE = 12  # read IQ 8 B + write qad 4 B (pulse table ~0.1 B/sample ignored)
 
 
@@ -432,7 +436,8 @@ def main():
     dense = float(np.mean(dense_ms))
     achieved = ALG_BYTES_PER_SAMPLE * n / (dense * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_fsk_fast<F32,WRITE,STATS> (demod + tile statistics)" if args.center == "detect"
+                "traffic": (TRAFFIC_B_PER_SAMPLE[args.center] * n) if TRAFFIC_B_PER_SAMPLE[args.center] else None, "traffic_source": TRAFFIC_SOURCE,
+                "kernel": "k_fsk_fast<F32,WRITE,STATS> (demod + tile statistics)" if args.center == "detect"
                 else "k_fsk_fast<F32,DIGITIZE,WRITE> (fused demod + classify + runs)", "kernel_ms": dense,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_SAMPLE * n, "peak_source": peak_src,
                 "kernel_share_of_step": dense / ms_per_step}

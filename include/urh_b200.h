@@ -175,6 +175,14 @@ int urh_costas_halo_samples(void);
 int urh_costas_shard_speculate(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int first_shard, float noise_mag,
                                int loop_order, float bandwidth, float* d_out);
 int urh_costas_shard_resolve(urh_ctx* ctx, const float* h_state_in, float* h_state_out);
+/* replaces ProtocolAnalyzer._ppseq_to_bits (ProtocolAnalyzer.py:323-414): pulse table -> bits / pauses / bit_sample_pos.
+ * d_rows = int64[k,2] on the device, NULL = the table the last digitizer call left in the context.  Results stay in the
+ * context until the next call.  Message m = bits[off[m]:off[m+1]]; its sample positions are pos[off[m]+2m : off[m+1]+2m+2]
+ * (one entry fewer for a last message that no pause row closes). */
+int urh_ppseq_to_bits(urh_ctx* ctx, const int64_t* d_rows, int64_t k, uint32_t samples_per_symbol, uint8_t bits_per_symbol,
+                      int pause_threshold, int write_pos, int64_t* n_msgs, int64_t* n_bits, int64_t* n_pos);
+int urh_fetch_bits(urh_ctx* ctx, uint8_t* h_bits, int64_t* h_msg_off, int64_t* h_pauses, int64_t* h_pos);
+const uint8_t* urh_bits_device_ptr(urh_ctx* ctx);
 /* NCCL (dlopen'ed libnccl.so.2): id from rank 0 is distributed by the launcher plumbing */
 int urh_nccl_unique_id(char* out128);
 int urh_nccl_init(urh_ctx* ctx, const char* id128, int rank, int world);

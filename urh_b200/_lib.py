@@ -106,6 +106,9 @@ SIGNATURES = {
     "urh_costas_halo_samples": (i32, []),
     "urh_costas_shard_speculate": (i32, [vp, vp, i32, i64, i32, f32, i32, f32, vp]),
     "urh_costas_shard_resolve": (i32, [vp, vp, vp]),
+    "urh_ppseq_to_bits": (i32, [vp, vp, i64, u32, u8, i32, i32, vp, vp, vp]),
+    "urh_fetch_bits": (i32, [vp, vp, vp, vp, vp]),
+    "urh_bits_device_ptr": (vp, [vp]),
     "urh_nccl_unique_id": (i32, [vp]),
     "urh_nccl_init": (i32, [vp, vp, i32, i32]),
     "urh_nccl_destroy": (i32, [vp]),

@@ -362,7 +362,7 @@ __device__ __forceinline__ void hist_flush(HistCache& hc, unsigned int* s_hist, 
 // Tiles strictly between win[0] and win[1] lie entirely inside the rank window: every kept sample counts, no rank
 // bookkeeping, no prefix reads.  One warp per tile, grid-stride, eight 512-byte rows in flight per warp.
 template <bool SMEM, bool FAST>
-__global__ void __launch_bounds__(256) k_hist_interior(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ win,
+__global__ void __launch_bounds__(256, 4) k_hist_interior(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ win,
                                                       const float* __restrict__ g_fe, float scale, int nbins,
                                                       unsigned long long* __restrict__ hist, int edges_in_smem) {
     extern __shared__ unsigned int s_dyn[];
@@ -387,24 +387,25 @@ __global__ void __launch_bounds__(256) k_hist_interior(const float* __restrict__
             const int64_t base = t * URH_TILE;   // interior tiles are full tiles (t < last tile)
             if (vec) {
                 const float4* p = (const float4*)(x + base) + lane;
-                constexpr int ITERS = URH_TILE / 128;
-                float4 cur[4], nxt[4];
+                constexpr int ITERS = URH_TILE / 128, RB = 2;   // RB rows being binned + RB rows in flight
+                float4 cur[RB], nxt[RB];
 #pragma unroll
-                for (int j = 0; j < 4; j++) cur[j] = __ldg(p + j * 32);
-                for (int it = 0; it < ITERS; it += 4) {
-                    if (it + 4 < ITERS) {
+                for (int j = 0; j < RB; j++) cur[j] = __ldg(p + j * 32);
+#pragma unroll 1
+                for (int it = 0; it < ITERS; it += RB) {
+                    if (it + RB < ITERS) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) nxt[j] = __ldg(p + (it + 4 + j) * 32);
+                        for (int j = 0; j < RB; j++) nxt[j] = __ldg(p + (it + RB + j) * 32);
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
+                    for (int j = 0; j < RB; j++) {
                         hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(cur[j].x));
                         hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(cur[j].y));
                         hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(cur[j].z));
                         hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(cur[j].w));
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) cur[j] = nxt[j];
+                    for (int j = 0; j < RB; j++) cur[j] = nxt[j];
                 }
             } else {
                 for (int j = lane; j < URH_TILE; j += 32) hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(x[base + j]));

@@ -54,6 +54,10 @@ struct urh_ctx {
     void* shard_state;
     // NCCL (nccl.cu)
     int64_t costas_stats[3];
+    // urh_ppseq_to_bits results (arena)
+    int bits_valid;
+    int64_t bits_nmsg, bits_total, bits_npos;
+    void *bits_ptr, *bits_msg_off, *bits_pauses, *bits_pos;
     const void* center_ts;
     const void* center_x;
     int64_t center_n;

@@ -30,6 +30,7 @@ extern "C" int urh_ctx_create(int device, urh_ctx** out) {
     ctx->shard_tiles = nullptr;
     ctx->shard_staging = nullptr;
     ctx->shard_state = nullptr;
+    ctx->bits_valid = 0;
     ctx->center_prefix = nullptr;
     ctx->center_ts = nullptr;
     ctx->center_x = nullptr;
@@ -217,6 +218,7 @@ void urh_arena_reset(urh_ctx* ctx) {
     ctx->arena_used = 0;
     ctx->arena_need = 0;
     ctx->center_prefix = nullptr;  // the detect_center tile table lived in the arena
+    ctx->bits_valid = 0;           // so did the bit arrays
 }
 
 int urh_arena_alloc(urh_ctx* ctx, size_t bytes, void** out) {

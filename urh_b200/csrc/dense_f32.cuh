@@ -8,6 +8,12 @@
 struct SrcQad {  // grab_pulse_lens on a demodulated array
     template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C) { return urh_classify((float)s, C); }
 };
+struct SrcQad2 {  // the same for a binary digitizer (order 2): no threshold loop, no branches
+    template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C) {
+        const int c = ((float)s <= C.thr[0]) ? 0 : 1;
+        return ((float)s == C.noise_value) ? -1 : c;
+    }
+};
 struct SrcAbove {  // segment_messages_from_magnitudes: class 1 = above noise (auto_interpretation.pyx:79)
     template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C) { return (s > (T)C.thr[0]) ? 1 : 0; }
 };

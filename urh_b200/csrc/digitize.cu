@@ -319,8 +319,12 @@ extern "C" int urh_grab_pulse_lens(urh_ctx* ctx, const float* d_qad, int64_t n, 
     const unsigned grid = (unsigned)urh_div_up(ntiles, URH_WARPS_PER_BLOCK);
     const int vec_in = (((uintptr_t)d_qad % 8) == 0) ? 1 : 0;
     URH_PROF_BEGIN(ctx);
-    URH_LAUNCH(ctx, (k_dense_f32<SrcQad, float>), grid, URH_WARPS_PER_BLOCK * 32, 0, d_qad, n, vec_in, cls, tol, tiles,
-               staging, cap, d_init, host_classify(0.0f, cls));
+    if (cls.order == 2)
+        URH_LAUNCH(ctx, (k_dense_f32<SrcQad2, float>), grid, URH_WARPS_PER_BLOCK * 32, 0, d_qad, n, vec_in, cls, tol, tiles,
+                   staging, cap, d_init, host_classify(0.0f, cls));
+    else
+        URH_LAUNCH(ctx, (k_dense_f32<SrcQad, float>), grid, URH_WARPS_PER_BLOCK * 32, 0, d_qad, n, vec_in, cls, tol, tiles,
+                   staging, cap, d_init, host_classify(0.0f, cls));
     URH_PROF_END(ctx);
     return digitize_finish(ctx, n, tol, mod_type == URH_MOD_ASK, samples_per_symbol, tiles, staging, cap, d_init, k);
 }
@@ -434,8 +438,13 @@ extern "C" int urh_shard_dense_qad(urh_ctx* ctx, const float* d_qad, int64_t n, 
     URH_CUDA(ctx, cudaMemsetAsync(d_init, 0, 16, ctx->stream));
     const int vec_in = (((uintptr_t)d_qad % 8) == 0) ? 1 : 0;
     URH_PROF_BEGIN(ctx);
-    URH_LAUNCH(ctx, (k_dense_f32<SrcQad, float>), (unsigned)urh_div_up(ntiles, URH_WARPS_PER_BLOCK), URH_WARPS_PER_BLOCK * 32, 0, d_qad, n,
-               vec_in, cls, tol, tiles, staging, cap, d_init, host_classify(0.0f, cls));
+    const unsigned grid = (unsigned)urh_div_up(ntiles, URH_WARPS_PER_BLOCK);
+    if (cls.order == 2)
+        URH_LAUNCH(ctx, (k_dense_f32<SrcQad2, float>), grid, URH_WARPS_PER_BLOCK * 32, 0, d_qad, n, vec_in, cls, tol, tiles, staging, cap,
+                   d_init, host_classify(0.0f, cls));
+    else
+        URH_LAUNCH(ctx, (k_dense_f32<SrcQad, float>), grid, URH_WARPS_PER_BLOCK * 32, 0, d_qad, n, vec_in, cls, tol, tiles, staging, cap,
+                   d_init, host_classify(0.0f, cls));
     URH_PROF_END(ctx);
     ctx->shard_tiles = tiles;
     ctx->shard_staging = staging;

@@ -140,6 +140,40 @@ def demod_center_digitize(samples, noise_mag: float, mod_type: str, tolerance: i
     return center, rows
 
 
+def ppseq_to_bits(ppseq, samples_per_symbol: int, bits_per_symbol: int = 1, write_bit_sample_pos: bool = True,
+                  pause_threshold: int = 8, ctx=None):
+    """ProtocolAnalyzer._ppseq_to_bits (ProtocolAnalyzer.py:323-414) on the GPU.  ``ppseq``: int64[k,2] numpy array or
+    DeviceArray, or an int k = "the first k rows of the table the last digitizer call left on the device" (no copy).
+    Returns flat arrays: (bits uint8[B], msg_off int64[M+1], pauses int64[M], pos int64[P] or None); message m is
+    bits[msg_off[m]:msg_off[m+1]], its bit_sample_pos pos[msg_off[m] + 2m : msg_off[m+1] + 2m + 2] (the last message has
+    one trailing entry instead of two when no pause row closes it)."""
+    if isinstance(ppseq, (int, np.integer)):
+        ctx = ctx or _lib.default_context()
+        ptr, k = 0, int(ppseq)
+    elif isinstance(ppseq, DeviceArray):
+        ctx, ptr, k = ppseq.ctx, ppseq.ptr, len(ppseq)
+        if ppseq.dtype != np.int64:
+            raise ValueError("pulse table must be int64[k, 2]")
+    else:
+        rows = np.ascontiguousarray(ppseq, dtype=np.int64).reshape(-1, 2)
+        ctx = ctx or _lib.default_context()
+        k = len(rows)
+        keep = to_device(rows, ctx) if k else None
+        ptr = keep.ptr if k else 0
+        if k == 0:
+            return np.zeros(0, np.uint8), np.zeros(1, np.int64), np.zeros(0, np.int64), (np.zeros(0, np.int64) if write_bit_sample_pos else None)
+    m, b, p = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    ctx.check(ctx.lib.urh_ppseq_to_bits(ctx.handle, C.c_void_p(ptr), k, int(samples_per_symbol), int(bits_per_symbol), int(pause_threshold),
+                                        int(bool(write_bit_sample_pos)), C.byref(m), C.byref(b), C.byref(p)))
+    bits = np.empty(b.value, np.uint8)
+    off = np.zeros(m.value + 1, np.int64)
+    pauses = np.empty(m.value, np.int64)
+    pos = np.empty(p.value, np.int64) if write_bit_sample_pos else None
+    ctx.check(ctx.lib.urh_fetch_bits(ctx.handle, bits.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                                     pauses.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p) if pos is not None else None))
+    return bits, off, pauses, pos
+
+
 # ---- modulator ------------------------------------------------------------------------------------------------
 def get_oqpsk_bits(original_bits) -> np.ndarray:
     """signal_functions.pyx:179-193 (host; a bit shuffle on a few thousand bits)."""

@@ -56,7 +56,7 @@ class ProtocolAnalyzer(object):
         ppseq = signal_functions.grab_pulse_lens(
             qad, signal.center, signal.tolerance, signal.modulation_type, signal.samples_per_symbol,
             signal.bits_per_symbol, signal.center_spacing)
-        bit_data, pauses, bit_sample_pos = self._ppseq_to_bits(
+        bit_data, pauses, bit_sample_pos = self._ppseq_to_bits_device(
             ppseq, signal.samples_per_symbol, signal.bits_per_symbol, pause_threshold=signal.pause_threshold)
         if signal.message_length_divisor > 1 and signal.modulation_type == "ASK":
             self._ensure_message_length_multiple(bit_data, signal.samples_per_symbol, pauses, bit_sample_pos, signal.message_length_divisor)
@@ -64,6 +64,22 @@ class ProtocolAnalyzer(object):
             middle = bit_sample_pos[i][int(len(bits) / 2)]
             rssi = np.mean(signal.iq_array.subarray(middle, middle + signal.samples_per_symbol).magnitudes_normalized)
             self.messages.append(LiteMessage(bits, pause, bit_sample_pos[i], rssi))
+
+    @staticmethod
+    def _ppseq_to_bits_device(ppseq, samples_per_symbol, bits_per_symbol, write_bit_sample_pos=True, pause_threshold=8):
+        """_ppseq_to_bits with the row loop on the GPU (bits.cu); same return structure as the reference's."""
+        bits, off, pause_arr, pos = signal_functions.ppseq_to_bits(ppseq, samples_per_symbol, bits_per_symbol, write_bit_sample_pos,
+                                                                   pause_threshold)
+        n_msgs = len(pause_arr)
+        all_bits = [array.array("B", bits[off[m]:off[m + 1]].tobytes()) for m in range(n_msgs)]
+        pauses = array.array("L", [int(v) for v in pause_arr])
+        all_positions = []
+        if write_bit_sample_pos:
+            for m in range(n_msgs):
+                lo = off[m] + 2 * m
+                hi = min(off[m + 1] + 2 * m + 2, len(pos))
+                all_positions.append(array.array("L", pos[lo:hi].astype(np.uint64).tobytes()))
+        return all_bits, pauses, all_positions
 
     @staticmethod
     def _ensure_message_length_multiple(bit_data, samples_per_symbol, pauses, bit_sample_pos, divisor):
