@@ -37,8 +37,8 @@ TOL = 5
 CENTER = 0.0
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per sample, from the ncu --set full captures in profiles/
 # (taken at 2^28 samples; the kernels stream, so DRAM bytes scale with n)
-TRAFFIC_B_PER_SAMPLE = {"detect": (2.147530e9 + 1.026364e9) / (1 << 28), "given": None}
-TRAFFIC_SOURCE = "profiles/r01_ncu_detect_m_summary.txt (ncu --set full at 2^28 samples, scaled by n)"
+TRAFFIC_B_PER_SAMPLE = {"detect": (2.147530e9 + 1.026364e9) / (1 << 28), "given": (2.152927e9 + 1.030241e9) / (1 << 28)}
+TRAFFIC_SOURCE = "profiles/r01_ncu_detect_m_summary.txt / r01_ncu_fast_g_summary.txt (ncu --set full at 2^28 samples, scaled by n)"
 ALG_BYTES_PER_SAMPLE = 12  # read IQ 8 B + write qad 4 B (pulse table ~0.1 B/sample ignored)
 
 

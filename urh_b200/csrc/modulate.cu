@@ -69,12 +69,12 @@ __global__ void k_fsk_corrections(const uint8_t* __restrict__ bits, const int64_
 __global__ void k_gfsk_freqs(const uint8_t* __restrict__ bits, const int64_t* __restrict__ bit_off,
                              const int64_t* __restrict__ smp_off, int nmsg, const __grid_constant__ ModParams P,
                              const double* __restrict__ gsum /* glen+1 prefix sums */, int glen, float* __restrict__ fp_table) {
-    const int m = blockIdx.y;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int m = blockIdx.y; m < nmsg; m += gridDim.y) {   // grid.y is capped at 65535
     const uint8_t* b = bits + bit_off[m];
     const int64_t nsym = (bit_off[m + 1] - bit_off[m]) / P.bps;
     const int64_t nval = nsym * P.sps;
     float* out = fp_table + 2 * smp_off[m];
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nval; k += stride) {
         // np.convolve(longer, shorter, 'same'): centred on the longer operand
         const int64_t t = (nval >= glen) ? k + (glen - 1) / 2 : k + (nval - 1) / 2;
@@ -94,29 +94,44 @@ __global__ void k_gfsk_freqs(const uint8_t* __restrict__ bits, const int64_t* __
         }
         out[2 * k] = (float)acc;
     }
+    }
 }
 
-// GFSK serial phase recurrence, one thread per message (pyx:220-224)
-__global__ void k_gfsk_phases(const int64_t* __restrict__ bit_off, const int64_t* __restrict__ smp_off, int nmsg,
-                              const __grid_constant__ ModParams P, float* __restrict__ fp_table) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= nmsg) return;
-    const int64_t nsym = (bit_off[m + 1] - bit_off[m]) / P.bps;
-    const int64_t nval = nsym * P.sps;
-    float* tab = fp_table + 2 * smp_off[m];
-    if (nval <= 0) return;
+// GFSK phase recurrence (pyx:220-224): phases[i+1] = float32(2*pi*t[i]*(f[i] - f[i+1]) + phases[i]) is a sequential
+// float32 accumulation, so it stays serial per message -- but only the rounding chain: one WARP per message computes the
+// 32 increments of a block in parallel (coalesced reads), then folds them in order from registers.
+__global__ void __launch_bounds__(128) k_gfsk_phases(const int64_t* __restrict__ bit_off, const int64_t* __restrict__ smp_off, int nmsg,
+                                                    const __grid_constant__ ModParams P, float* __restrict__ fp_table) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double two_pi = 2.0 * M_PI;
-    float ph = P.phi;
-    tab[1] = ph;
-    float fcur = tab[0];
-    for (int64_t i = 0; i + 1 < nval; i++) {
-        const float fnext = tab[2 * (i + 1)];
-        // t = np.arange(start, ..., dtype=float32) / sample_rate: float32 index, float32 division
-        const float t = __fdiv_rn(__ll2float_rn((long long)i + (long long)P.start), P.sample_rate);
-        const double v = __dadd_rn(__dmul_rn(__dmul_rn(two_pi, (double)t), (double)__fsub_rn(fcur, fnext)), (double)ph);
-        ph = (float)v;
-        tab[2 * (i + 1) + 1] = ph;
-        fcur = fnext;
+    for (int64_t m = warp; m < nmsg; m += nwarps) {
+        const int64_t nsym = (bit_off[m + 1] - bit_off[m]) / P.bps;
+        const int64_t nval = nsym * P.sps;
+        if (nval <= 0) continue;
+        float* tab = fp_table + 2 * smp_off[m];
+        float ph = P.phi;
+        if (lane == 0) tab[1] = ph;
+        for (int64_t base = 0; base + 1 < nval; base += 32) {
+            const int64_t i = base + lane;
+            const bool valid = i + 1 < nval;
+            double c = 0.0;
+            if (valid) {
+                const float fcur = tab[2 * i], fnext = tab[2 * (i + 1)];
+                // t = np.arange(start, ..., dtype=float32) / sample_rate: float32 index, float32 division
+                const float t = __fdiv_rn(__ll2float_rn((long long)i + (long long)P.start), P.sample_rate);
+                c = __dmul_rn(__dmul_rn(two_pi, (double)t), (double)__fsub_rn(fcur, fnext));
+            }
+            const int count = (int)min((int64_t)32, nval - 1 - base);
+            float mine = 0.0f;
+            for (int l = 0; l < count; l++) {
+                const double cl = __shfl_sync(0xffffffffu, c, l);
+                ph = (float)__dadd_rn(cl, (double)ph);
+                if (lane == l) mine = ph;
+            }
+            if (valid) tab[2 * (i + 1) + 1] = mine;
+        }
     }
 }
 
@@ -131,13 +146,13 @@ __global__ void k_modulate(const uint8_t* __restrict__ bits, const int64_t* __re
                            const int64_t* __restrict__ sym_off, const int64_t* __restrict__ smp_off,
                            const int64_t* __restrict__ out_off, int nmsg, const __grid_constant__ ModParams P,
                            const float* __restrict__ corr, const float* __restrict__ fp_table, OUT* __restrict__ out) {
-    const int m = blockIdx.y;
+    const double two_pi = 2.0 * M_PI;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int m = blockIdx.y; m < nmsg; m += gridDim.y) {   // grid.y is capped at 65535
     const uint8_t* b = bits + bit_off[m];
     const int64_t nsym = (bit_off[m + 1] - bit_off[m]) / P.bps;
     const int64_t nval = nsym * P.sps;
     OUT* o = out + 2 * out_off[m];
-    const double two_pi = 2.0 * M_PI;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nval; i += stride) {
         const int64_t s = i / P.sps;
         const uint32_t idx = symbol_index(b, s, P.bps);
@@ -170,6 +185,7 @@ __global__ void k_modulate(const uint8_t* __restrict__ bits, const int64_t* __re
         }
         o[2 * i] = mod_cast<OUT>(I);
         o[2 * i + 1] = mod_cast<OUT>(Q);
+    }
     }
 }
 
@@ -226,7 +242,7 @@ extern "C" int urh_modulate_batch(urh_ctx* ctx, const uint8_t* d_bits, const int
         URH_LAUNCH(ctx, k_fsk_corrections, (unsigned)urh_div_up(nmsg, 64), 64, 0, d_bits, d_bit_off, d_sym_off, nmsg, P, corr);
     }
     const unsigned gx = (unsigned)max((int64_t)1, min(urh_div_up(max_samples, 256), (int64_t)ctx->sm_count * 8));
-    const dim3 grid(gx, (unsigned)nmsg);
+    const dim3 grid(gx, (unsigned)min(nmsg, 65535));
     if (mod_type == URH_MOD_GFSK) {
         if (!h_gauss_fir || gauss_len <= 0) URH_FAIL(ctx, URH_ERR_INVALID, "GFSK needs the gaussian filter taps");
         URH_CHECK(urh_arena(ctx, (size_t)smp_off[nmsg] * 2 + 2, &fp_table));
@@ -236,7 +252,8 @@ extern "C" int urh_modulate_batch(urh_ctx* ctx, const uint8_t* d_bits, const int
         URH_CUDA(ctx, cudaMemcpyAsync(d_gsum, gsum.data(), (gauss_len + 1) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         URH_LAUNCH(ctx, k_gfsk_freqs, grid, 256, 0, d_bits, d_bit_off, d_smp_off, nmsg, P, d_gsum, gauss_len, fp_table);
-        URH_LAUNCH(ctx, k_gfsk_phases, (unsigned)urh_div_up(nmsg, 64), 64, 0, d_bit_off, d_smp_off, nmsg, P, fp_table);
+        URH_LAUNCH(ctx, k_gfsk_phases, (unsigned)min((int64_t)urh_div_up(nmsg, 4), (int64_t)ctx->sm_count * 16), 128, 0, d_bit_off, d_smp_off, nmsg, P,
+                   fp_table);
     }
     if (out_dtype == URH_DT_F32)
         URH_LAUNCH(ctx, k_modulate<float>, grid, 256, 0, d_bits, d_bit_off, d_sym_off, d_smp_off, d_out_off, nmsg, P, corr, fp_table, (float*)d_out);

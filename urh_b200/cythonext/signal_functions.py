@@ -219,25 +219,36 @@ def modulate_batch(messages, samples_per_symbol, modulation_type, parameters, bi
     if mod == "oqpsk":
         assert bits_per_symbol == 2
     ctx = _lib.default_context()
-    msgs = []
-    for bits in messages:
-        b = np.ascontiguousarray(np.asarray(bits, dtype=np.uint8))
-        if mod == "oqpsk" and len(b):
-            b = np.ascontiguousarray(get_oqpsk_bits(b)[: len(b)])  # only the first len(bits) shuffled bits are used
-        msgs.append(b)
-    nmsg = len(msgs)
-    pauses = [int(p) for p in (pauses if hasattr(pauses, "__len__") else [pauses] * nmsg)]
-    bit_off = np.zeros(nmsg + 1, dtype=np.int64)
-    out_off = np.zeros(nmsg + 1, dtype=np.int64)
-    for m, b in enumerate(msgs):
-        bit_off[m + 1] = bit_off[m] + len(b)
-        nsym = int(len(b) // bits_per_symbol)
-        out_off[m + 1] = out_off[m] + nsym * int(samples_per_symbol) + pauses[m]
+    rect = isinstance(messages, np.ndarray) and messages.ndim == 2 and mod != "oqpsk"
+    if rect:
+        # equal-length messages given as one [nmsg, nbits] array: no per-message Python work
+        flat = np.ascontiguousarray(messages, dtype=np.uint8)
+        nmsg, per = flat.shape
+        pauses = np.asarray(pauses if hasattr(pauses, "__len__") else [pauses] * nmsg, dtype=np.int64)
+        bit_off = np.arange(nmsg + 1, dtype=np.int64) * per
+        out_off = np.zeros(nmsg + 1, dtype=np.int64)
+        np.cumsum(int(per // bits_per_symbol) * int(samples_per_symbol) + pauses, out=out_off[1:])
+        msgs = None
+    else:
+        msgs = []
+        for bits in messages:
+            b = np.ascontiguousarray(np.asarray(bits, dtype=np.uint8))
+            if mod == "oqpsk" and len(b):
+                b = np.ascontiguousarray(get_oqpsk_bits(b)[: len(b)])  # only the first len(bits) shuffled bits are used
+            msgs.append(b)
+        nmsg = len(msgs)
+        pauses = [int(p) for p in (pauses if hasattr(pauses, "__len__") else [pauses] * nmsg)]
+        bit_off = np.zeros(nmsg + 1, dtype=np.int64)
+        out_off = np.zeros(nmsg + 1, dtype=np.int64)
+        for m, b in enumerate(msgs):
+            bit_off[m + 1] = bit_off[m] + len(b)
+            nsym = int(len(b) // bits_per_symbol)
+            out_off[m + 1] = out_off[m] + nsym * int(samples_per_symbol) + pauses[m]
     total = int(out_off[-1])
     params = np.ascontiguousarray(np.asarray(parameters, dtype=np.float32))
     d_out = DeviceArray(ctx, (total, 2), dtype)
     if total and bit_off[-1] > 0:
-        d_bits = to_device(np.concatenate(msgs) if nmsg else np.zeros(0, np.uint8), ctx)
+        d_bits = to_device(flat.reshape(-1) if rect else (np.concatenate(msgs) if nmsg else np.zeros(0, np.uint8)), ctx)
         gfir = gauss_fir(sample_rate, samples_per_symbol, bt=gauss_bt, filter_width=filter_width) if mod == "gfsk" else None
         ctx.check(ctx.lib.urh_modulate_batch(
             ctx.handle, C.c_void_p(d_bits.ptr), bit_off.ctypes.data_as(C.c_void_p), out_off.ctypes.data_as(C.c_void_p), nmsg,
