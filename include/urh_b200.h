@@ -175,6 +175,14 @@ int urh_costas_halo_samples(void);
 int urh_costas_shard_speculate(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int first_shard, float noise_mag,
                                int loop_order, float bandwidth, float* d_out);
 int urh_costas_shard_resolve(urh_ctx* ctx, const float* h_state_in, float* h_state_out);
+/* the sample-rate part of AutoInterpretation.detect_modulation (AutoInterpretation.py:151-208) for one message
+ * (d_data = complex64[n] on the device): zero removal, normalisation, the two Haar wavelet transforms (cuFFT for the FFTs),
+ * variances before/after the median filter and the spectrum features of the FSK test.  h_feat[8] = {n_nonzero, P, L, var_mag,
+ * var_norm_mag, var_filtered_mag, var_filtered_norm_mag, |max|}; h_spec[23] = {arg-max bin, value, best bin >= 10 away,
+ * value, the 19 values around the arg-max}.  urh_cwt_haar replaces Wavelet.cwt_haar (Wavelet.py:15-43). */
+int urh_modulation_features(urh_ctx* ctx, const float* d_data, int64_t n, int wavelet_scale, int median_k, double* h_feat,
+                            double* h_spec);
+int urh_cwt_haar(urh_ctx* ctx, const void* d_x, int is_c128, int64_t n, int scale, double* d_out, int64_t* out_len);
 /* replaces ProtocolAnalyzer._ppseq_to_bits (ProtocolAnalyzer.py:323-414): pulse table -> bits / pauses / bit_sample_pos.
  * d_rows = int64[k,2] on the device, NULL = the table the last digitizer call left in the context.  Results stay in the
  * context until the next call.  Message m = bits[off[m]:off[m+1]]; its sample positions are pos[off[m]+2m : off[m+1]+2m+2]

@@ -328,3 +328,60 @@ def apply_bandpass_filter(data, f_low, f_high, filter_bw=0.08):
     if len(h) < 8 * math.log(math.sqrt(len(data))):
         return np.convolve(data, h, "same")
     return fft_convolve_1d(data, h)
+
+
+# ---- Haar wavelet / modulation detection (Wavelet.py:7-43, AutoInterpretation.py:151-208) -------------------------------
+def normalized_haar_wavelet(omega, scale):
+    scaled = omega[:] / scale
+    scaled[0] = 1.0  # omega[0] == 0: avoid 0/0, the numerator is 0 there anyway
+    return (1j * np.square(-1 + np.exp(0.5j * omega))) / scaled
+
+
+def cwt_haar(x, scale=10):
+    num = 2 ** int(np.log2(len(x)))  # truncate to a power of two
+    x = x[0:num]
+    x_hat = np.fft.fft(x)
+    f = 2.0 * np.pi / num
+    omega = f * np.concatenate((np.arange(0, num // 2), np.arange(num // 2, num) * -1))
+    psi_hat = np.sqrt(2.0 * np.pi * scale) * normalized_haar_wavelet(scale * omega, scale)
+    W = np.fft.ifft(x_hat * psi_hat)
+    return W[2 * scale: -2 * scale]
+
+
+def modulation_features(data, wavelet_scale=4, median_filter_order=11):
+    """the quantities detect_modulation decides on: (n_nonzero, var_mag, var_norm_mag, var_filtered_mag,
+    var_filtered_norm_mag, fsk_test or None) -- None where the reference returns before computing them"""
+    n_data = len(data)
+    data = data[np.abs(data) > 0]
+    if len(data) == 0 or n_data - len(data) > 3:
+        return len(data), None
+    data = data / np.abs(np.max(data))
+    mag = np.abs(cwt_haar(data, scale=wavelet_scale))
+    if len(mag) == 0:
+        return len(data), None
+    norm_mag = np.abs(cwt_haar(data / np.abs(data), scale=wavelet_scale))
+    fft = np.fft.fft(data[0: 2 ** int(np.log2(len(data)))])
+    fft = np.abs(np.fft.fftshift(fft))
+    ten = np.argsort(fft)[::-1][0:10]
+    fsk = bool(any(abs(i - ten[0]) >= 10 and fft[i] >= 100 for i in ten))
+    return len(data), (float(np.var(mag)), float(np.var(norm_mag)), float(np.var(median_filter(mag, k=median_filter_order))),
+                       float(np.var(median_filter(norm_mag, k=median_filter_order))), fsk)
+
+
+def detect_modulation(data, wavelet_scale=4, median_filter_order=11):
+    n_data = len(data)
+    nz, feat = modulation_features(data, wavelet_scale, median_filter_order)
+    if nz == 0:
+        return None
+    if n_data - nz > 3:
+        return "OOK"
+    if feat is None:
+        return None
+    var_mag, var_norm_mag, var_filtered_mag, var_filtered_norm_mag, fsk = feat
+    if all(v < 0.15 for v in (var_mag, var_norm_mag, var_filtered_mag, var_filtered_norm_mag)):
+        return "OOK"
+    if var_mag > 1.5 * var_norm_mag:
+        return "ASK"
+    if var_mag > 10 * var_filtered_mag:
+        return "PSK"
+    return "FSK" if fsk else "OOK"

@@ -134,22 +134,46 @@ def merge_message_segments_for_ook(segments: list):
 
 
 # ---- modulation detection (AutoInterpretation.py:151-223) --------------------------------------------------------
-def detect_modulation(data: np.ndarray, wavelet_scale=4, median_filter_order=11) -> str:
+def modulation_features(data, wavelet_scale=4, median_filter_order=11):
+    """The sample-rate part of detect_modulation on the GPU (modulation.cu): -> (feat[8], spec[23]), see urh_b200.h."""
+    on_device = isinstance(data, DeviceArray)
+    if on_device:
+        ctx, d = data.ctx, data
+        if data.dtype != np.complex64:
+            raise ValueError("complex64 message expected")
+    else:
+        data = np.ascontiguousarray(data, dtype=np.complex64)
+        ctx = _lib.default_context()
+        d = to_device(data.view(np.float32), ctx) if len(data) else None
+    feat, spec = np.zeros(8), np.full(23, -1.0)
+    if len(data):
+        ctx.check(ctx.lib.urh_modulation_features(ctx.handle, C.c_void_p(d.ptr), len(data), int(wavelet_scale), int(median_filter_order),
+                                                  feat.ctypes.data_as(C.c_void_p), spec.ctypes.data_as(C.c_void_p)))
+    return feat, spec
+
+
+def _fsk_peak_test(spec) -> bool:
+    """`any(abs(i - top) >= 10 and fft[i] >= 100 for i in ten_greatest)` from the device's spectrum features: the largest
+    value >= 10 bins from the arg-max is one of the ten greatest iff fewer than ten bins (all of them within 9 bins of the
+    arg-max) exceed it; every other far bin among the ten greatest is smaller still."""
+    far_index, far_value = int(spec[2]), spec[3]
+    if far_index < 0 or far_value < 100:
+        return False
+    return int(np.sum(spec[4:23] > far_value)) < 10
+
+
+def detect_modulation(data, wavelet_scale=4, median_filter_order=11) -> str:
+    """AutoInterpretation.py:151-208; the decision thresholds are the reference's, the features come from the GPU."""
     n_data = len(data)
-    data = data[np.abs(data) > 0]
-    if len(data) == 0:
+    feat, spec = modulation_features(data, wavelet_scale, median_filter_order)
+    n_nonzero = int(feat[0])
+    if n_nonzero == 0:
         return None
-    if n_data - len(data) > 3:
+    if n_data - n_nonzero > 3:
         return "OOK"
-    data = data / np.abs(np.max(data))
-    mag_wavlt = np.abs(Wavelet.cwt_haar(data, scale=wavelet_scale))
-    if len(mag_wavlt) == 0:
-        return None
-    norm_mag_wavlt = np.abs(Wavelet.cwt_haar(data / np.abs(data), scale=wavelet_scale))
-    var_mag = np.var(mag_wavlt)
-    var_norm_mag = np.var(norm_mag_wavlt)
-    var_filtered_mag = np.var(c_auto_interpretation.median_filter(mag_wavlt, k=median_filter_order))
-    var_filtered_norm_mag = np.var(c_auto_interpretation.median_filter(norm_mag_wavlt, k=median_filter_order))
+    if int(feat[2]) == 0:
+        return None  # message shorter than the wavelet's support
+    var_mag, var_norm_mag, var_filtered_mag, var_filtered_norm_mag = feat[3:7]
     if all(v < 0.15 for v in (var_mag, var_norm_mag, var_filtered_mag, var_filtered_norm_mag)):
         return "OOK"
     if var_mag > 1.5 * var_norm_mag:
@@ -157,13 +181,7 @@ def detect_modulation(data: np.ndarray, wavelet_scale=4, median_filter_order=11)
     if var_mag > 10 * var_filtered_mag:
         return "PSK"
     # FSK has at least two spectral peaks, a lone OOK pulse has one
-    fft = np.fft.fft(data[0: 2 ** int(np.log2(len(data)))])
-    fft = np.abs(np.fft.fftshift(fft))
-    ten = np.argsort(fft)[::-1][0:10]
-    top = ten[0]
-    if any(abs(i - top) >= 10 and fft[i] >= 100 for i in ten):
-        return "FSK"
-    return "OOK"
+    return "FSK" if _fsk_peak_test(spec) else "OOK"
 
 
 def detect_modulation_for_messages(signal, message_indices: list) -> str:

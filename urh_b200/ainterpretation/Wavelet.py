@@ -1,24 +1,34 @@
-"""Haar continuous wavelet transform in the frequency domain (reference: src/urh/ainterpretation/Wavelet.py:7-43).
+"""Haar continuous wavelet transform in the frequency domain (reference: src/urh/ainterpretation/Wavelet.py:7-43) on
+the GPU: forward FFT (float32 for complex64 input, as numpy >= 2 computes it; double otherwise), multiplication with the
+analytic Haar spectrum in complex128, inverse FFT in double (modulation.cu; cuFFT for the FFTs only)."""
+import ctypes as C
 
-Second-tier row of the scope table: per-message FFTs of at most a few million points.  Round 1
-keeps numpy's FFT on the host so that `detect_modulation` has exactly the reference's numerics; the cuFFT
-version is the planned replacement.
-"""
 import numpy as np
 
-
-def normalized_haar_wavelet(omega, scale):
-    scaled = omega[:] / scale
-    scaled[0] = 1.0  # omega[0] == 0: avoid 0/0, the numerator is 0 there anyway
-    return (1j * np.square(-1 + np.exp(0.5j * omega))) / scaled
+from .. import _lib
+from ..device import DeviceArray, to_device
 
 
-def cwt_haar(x: np.ndarray, scale=10):
-    num = 2 ** int(np.log2(len(x)))  # truncate to a power of two
-    x = x[0:num]
-    x_hat = np.fft.fft(x)
-    f = 2.0 * np.pi / num
-    omega = f * np.concatenate((np.arange(0, num // 2), np.arange(num // 2, num) * -1))
-    psi_hat = np.sqrt(2.0 * np.pi * scale) * normalized_haar_wavelet(scale * omega, scale)
-    W = np.fft.ifft(x_hat * psi_hat)
-    return W[2 * scale: -2 * scale]
+def cwt_haar(x, scale=10):
+    """-> complex128[P - 4*scale] with P = 2**floor(log2(len(x))) (numpy array)"""
+    on_device = isinstance(x, DeviceArray)
+    if on_device:
+        ctx, d = x.ctx, x
+        is_c128 = x.dtype == np.complex128
+        if x.dtype not in (np.complex64, np.complex128):
+            raise ValueError("cwt_haar on the device takes complex64 or complex128")
+    else:
+        x = np.asarray(x)
+        is_c128 = x.dtype != np.complex64
+        x = np.ascontiguousarray(x, dtype=np.complex128 if is_c128 else np.complex64)
+        ctx = _lib.default_context()
+        d = to_device(x.view(np.float64 if is_c128 else np.float32), ctx) if len(x) else None
+    n = len(x)
+    if n == 0:
+        raise ValueError("cwt_haar of an empty array")  # int(np.log2(0)) raises in the reference as well
+    num = 2 ** int(np.log2(n))
+    out_len = max(num - 4 * int(scale), 0)
+    out = DeviceArray(ctx, (max(out_len, 1),), np.complex128)
+    got = C.c_int64(0)
+    ctx.check(ctx.lib.urh_cwt_haar(ctx.handle, C.c_void_p(d.ptr), int(is_c128), n, int(scale), C.c_void_p(out.ptr), C.byref(got)))
+    return out.get()[: got.value]

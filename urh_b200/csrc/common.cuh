@@ -54,6 +54,10 @@ struct urh_ctx {
     void* shard_state;
     // NCCL (nccl.cu)
     int64_t costas_stats[3];
+    // cuFFT plans of detect_modulation / cwt_haar: [0] C2C, [1] Z2Z, batch 2, length mod_plan_n
+    int mod_plan[2];
+    int mod_plan_valid[2];
+    int64_t mod_plan_n[2];
     // urh_ppseq_to_bits results (arena)
     int bits_valid;
     int64_t bits_nmsg, bits_total, bits_npos;
@@ -112,6 +116,7 @@ static inline int urh_arena(urh_ctx* ctx, size_t count, T** out) {
     return rc;
 }
 int urh_ensure_pulses(urh_ctx* ctx, size_t rows);
+void urh_release_mod_plans(urh_ctx* ctx);  // modulation.cu
 int urh_ensure_stage(urh_ctx* ctx, size_t bytes);
 
 // read back `count` int64 scalars from device (synchronises the ctx stream)

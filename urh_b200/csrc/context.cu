@@ -31,6 +31,7 @@ extern "C" int urh_ctx_create(int device, urh_ctx** out) {
     ctx->shard_staging = nullptr;
     ctx->shard_state = nullptr;
     ctx->bits_valid = 0;
+    ctx->mod_plan_valid[0] = ctx->mod_plan_valid[1] = 0;
     ctx->center_prefix = nullptr;
     ctx->center_ts = nullptr;
     ctx->center_x = nullptr;
@@ -80,6 +81,7 @@ extern "C" void urh_ctx_destroy(urh_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    urh_release_mod_plans(ctx);
     for (auto& b : ctx->arena) cudaFree(b.ptr);
     if (ctx->pulses) cudaFree(ctx->pulses);
     if (ctx->shard_state) free(ctx->shard_state);
