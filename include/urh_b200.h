@@ -207,6 +207,7 @@ int urh_set_profiling(urh_ctx* ctx, int enabled);
 int urh_last_dense_ms(urh_ctx* ctx, float* ms);
 /* speculative Costas loop diagnostics of the last PSK demodulation: {chunks matched in O(1), chunks walked, samples stepped serially} */
 int urh_costas_stats(urh_ctx* ctx, int64_t* h_out3);
+int64_t urh_costas_last_redone(urh_ctx* ctx);
 /* packed (f32x2) division used by the FSK fast path vs __fdiv_rn on `count` random operand pairs */
 int urh_selftest_packed_div(urh_ctx* ctx, uint64_t seed, int64_t count, int64_t* mismatches, int64_t* tested);
 /* synthetic phase-continuous 2-FSK bursts + AWGN + noise-only gaps generated in HBM (SURVEY 8d recipe) */

@@ -152,27 +152,41 @@ __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ i
     if (k == 0) chunk_cnt[c] = total;
 }
 
-// pass 2: the chain.  src[c*CS_SEGS + j]: candidate index whose samples are the true ones in that segment, or 255
-// when the resolver wrote the true samples itself.
+// ---- pass 2: the chain ------------------------------------------------------------------------------------------------
+// A chain carries a loop state from chunk to chunk.  If the state equals a candidate's state at the chunk start (bitwise),
+// that candidate's run IS the run for the whole chunk: O(1).  Otherwise the state is stepped through the chunk segment by
+// segment until it meets a candidate checkpoint.  Tables (one set per chain family t):
+//   src[t][c*segs + j]   candidate whose samples are right in that segment, or 255 = "stepped here"
+//   segst[t][c*segs + j] the state at the start of a stepped segment (k_cs_fix recomputes those samples from it)
+// The chain itself is still serial, so it is run speculatively as well (pass 2a): the chunks are grouped into super-chunks
+// of CS_SUP chunks and one warp per (super-chunk, candidate k) runs the chain through the super-chunk ASSUMING it starts in
+// candidate k's start state.  Pass 2b (one warp) then only hops from super-chunk to super-chunk: the true state at a
+// super-chunk start almost always equals one of the assumptions (bitwise) -> take that chain's tables and end state; if
+// not, the warp runs the chain through that super-chunk itself (table family nbr).  Exactness is by construction as in
+// pass 1: a chain is only ever adopted when its starting state is bit-identical to the true one.
+#define CS_SUP 64
+
+struct CsTables {
+    uint8_t* src;     // [nbr + 1][nseg]
+    CsState* segst;   // [nbr + 1][nseg]
+    int64_t nseg;     // nchunks * segs
+};
+
+// one warp; returns the state after chunk hi-1.  acc[0..2] += {O(1) chunks, walked chunks, samples stepped}
 template <int DT>
-__global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, int64_t n, CsParams P, int64_t nchunks, int nbr,
-                                                   const CsState* __restrict__ ckpt, const int* __restrict__ nonnoise,
-                                                   const int* __restrict__ chunk_cnt, float* __restrict__ out, uint8_t* __restrict__ src,
-                                                   int64_t* __restrict__ stats, int first_shard, CsState st_in,
-                                                   CsState* __restrict__ st_out) {
-    const int lane = threadIdx.x;
-    // first shard: true state at the end of chunk 0 (exact run); later shards: the state handed over by the
-    // preceding shard, and chunk 0 is resolved like every other chunk
-    CsState st = first_shard ? ckpt[P.segs] : st_in;
-    if (first_shard && lane < P.segs) src[lane] = 0;
+__device__ CsState cs_chain(const void* __restrict__ iq, int64_t n, const CsParams& P, int64_t nchunks, int nbr,
+                            const CsState* __restrict__ ckpt, const int* __restrict__ nonnoise, const int* __restrict__ chunk_cnt,
+                            uint8_t* __restrict__ src, CsState* __restrict__ segst, int first_shard, int64_t lo, int64_t hi, CsState st,
+                            int64_t* acc) {
+    const int lane = threadIdx.x & 31;
     int64_t fast = 0, slow = 0, stepped = 0;
-    for (int64_t c0 = first_shard ? 1 : 0; c0 < nchunks; c0 += 32) {
+    for (int64_t c0 = lo; c0 < hi; c0 += 32) {
         // every lane prefetches the candidates' start/end states of chunk c0 + lane
         const int64_t cl = c0 + lane;
         CsState s0[CS_MAXBR], s1[CS_MAXBR];
 #pragma unroll
         for (int k = 0; k < CS_MAXBR; k++) {
-            if (k < nbr && cl < nchunks) {
+            if (k < nbr && cl < hi) {
                 const CsState* ck = ckpt + ((int64_t)k * nchunks + cl) * (P.segs + 1);
                 s0[k] = ck[0];
                 s1[k] = ck[P.segs];
@@ -180,8 +194,8 @@ __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, 
                 s0[k].freq = s0[k].phase = s1[k].freq = s1[k].phase = __int_as_float(0x7fc00000);
             }
         }
-        const int my_cnt = (cl < nchunks) ? chunk_cnt[cl] : 0;
-        const int todo = (int)min((int64_t)32, nchunks - c0);
+        const int my_cnt = (cl < hi) ? chunk_cnt[cl] : 0;
+        const int todo = (int)min((int64_t)32, hi - c0);
         for (int t = 0; t < todo; t++) {
             const int64_t c = c0 + t;
             const int ccnt = __shfl_sync(URH_FULL_MASK, my_cnt, t);
@@ -199,7 +213,7 @@ __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, 
                     e.phase = p1;
                 }
             }
-            if (match >= 0) {  // O(1): the candidate's run is the true run
+            if (match >= 0) {  // O(1): the candidate's run is the run
                 if (lane < P.segs) src[c * P.segs + lane] = (uint8_t)match;
                 st = e;
                 fast++;
@@ -211,7 +225,7 @@ __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, 
                 continue;
             }
             slow++;
-            // walk the chunk from the true state; lane 0 computes, the decision is broadcast
+            // walk the chunk; lane 0 computes, the decision is broadcast
             int merged = -1, jm = P.segs;
             for (int j = 0; j < P.segs; j++) {
                 const int cnt = nonnoise[c * P.segs + j];
@@ -219,37 +233,46 @@ __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, 
                     if (lane == 0) src[c * P.segs + j] = 0;
                     continue;
                 }
+                if (lane == 0) {
+                    src[c * P.segs + j] = 255;
+                    segst[c * P.segs + j] = st;
+                }
                 const int64_t a = c * P.chunk + (int64_t)j * CS_SEG;
-                // the warp stages the segment (coalesced) and evaluates the noise gate in parallel; lane 0 then
-                // advances the loop over the non-noise samples only
+                // the warp stages the whole segment at once (8 coalesced loads in flight per lane) and evaluates the noise
+                // gate in parallel; lane 0 then advances the loop over the non-noise samples only (the samples themselves
+                // are written by k_cs_fix)
+                float sre[CS_SEG / 32], sim[CS_SEG / 32];
+                unsigned smask[CS_SEG / 32];
+#pragma unroll
                 for (int g = 0; g < CS_SEG / 32; g++) {
                     const int64_t i = a + g * 32 + lane;
-                    float re = 0.f, im = 0.f;
-                    bool live = false;
-                    if (i < n && !(i == 0 && first_shard)) {
-                        cs_load<DT>(iq, i, re, im);
-                        live = !(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)) <= P.noise_sqrd);
-                        if (!live) out[i] = -4.0f;
-                    } else if (i == 0 && first_shard) {
-                        out[0] = 0.0f;
-                    }
-                    unsigned mask = __ballot_sync(URH_FULL_MASK, live);
+                    sre[g] = 0.f; sim[g] = 0.f;
+                    if (i < n && !(i == 0 && first_shard)) cs_load<DT>(iq, i, sre[g], sim[g]);
+                }
+#pragma unroll
+                for (int g = 0; g < CS_SEG / 32; g++) {
+                    const int64_t i = a + g * 32 + lane;
+                    const bool live = (i < n && !(i == 0 && first_shard)) &&
+                                      !(__fadd_rn(__fmul_rn(sre[g], sre[g]), __fmul_rn(sim[g], sim[g])) <= P.noise_sqrd);
+                    smask[g] = __ballot_sync(URH_FULL_MASK, live);
+                }
+#pragma unroll
+                for (int g = 0; g < CS_SEG / 32; g++) {
+                    unsigned mask = smask[g];
                     while (mask) {
                         const int l = __ffs(mask) - 1;
                         mask &= mask - 1;
-                        const float r1 = __shfl_sync(URH_FULL_MASK, re, l), i1 = __shfl_sync(URH_FULL_MASK, im, l);
+                        const float r1 = __shfl_sync(URH_FULL_MASK, sre[g], l), i1 = __shfl_sync(URH_FULL_MASK, sim[g], l);
                         if (lane == 0) {
                             float o;
                             cs_step(st, r1, i1, P, o);
-                            out[a + g * 32 + l] = o;
                         }
                     }
                 }
-                if (lane == 0) src[c * P.segs + j] = 255;
                 stepped += cnt;
                 st.freq = __shfl_sync(URH_FULL_MASK, st.freq, 0);
                 st.phase = __shfl_sync(URH_FULL_MASK, st.phase, 0);
-                // does the true state now coincide with a candidate checkpoint?
+                // does the state now coincide with a candidate checkpoint?
                 int m = -1;
                 if (lane < nbr) {
                     const CsState q = ckpt[((int64_t)lane * nchunks + c) * (P.segs + 1) + j + 1];
@@ -269,20 +292,140 @@ __global__ void __launch_bounds__(32) k_cs_resolve(const void* __restrict__ iq, 
             }
         }
     }
-    if (lane == 0 && st_out) *st_out = st;
-    if (lane == 0 && stats) {
-        stats[0] = fast;
-        stats[1] = slow;
-        stats[2] = stepped;
+    acc[0] += fast; acc[1] += slow; acc[2] += stepped;
+    return st;
+}
+
+// pass 2a: one warp per (super-chunk w, assumption k).  sup_end[w*nbr + k] = state after the super-chunk, sup_acc its counters.
+template <int DT>
+__global__ void __launch_bounds__(128) k_cs_chains(const void* __restrict__ iq, int64_t n, CsParams P, int64_t nchunks, int nbr,
+                                                  const CsState* __restrict__ ckpt, const int* __restrict__ nonnoise,
+                                                  const int* __restrict__ chunk_cnt, CsTables T, int first_shard, int64_t nsuper,
+                                                  CsState* __restrict__ sup_end, int64_t* __restrict__ sup_acc) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= nsuper * nbr) return;
+    const int64_t w = wid / nbr;
+    const int k = (int)(wid % nbr);
+    int64_t lo = w * CS_SUP;
+    const int64_t hi = min(nchunks, lo + CS_SUP);
+    int64_t acc[3] = {0, 0, 0};
+    CsState st;
+    uint8_t* src = T.src + (int64_t)k * T.nseg;
+    CsState* segst = T.segst + (int64_t)k * T.nseg;
+    if (w == 0 && first_shard) {
+        // the capture's first chunk is the one exact run (candidate 0 started from the loop's true initial state)
+        if (k != 0) return;
+        if (lane < P.segs) src[lane] = 0;
+        st = ckpt[P.segs];
+        lo = 1;
+    } else {
+        st = ckpt[((int64_t)k * nchunks + lo) * (P.segs + 1)];
+    }
+    st = cs_chain<DT>(iq, n, P, nchunks, nbr, ckpt, nonnoise, chunk_cnt, src, segst, first_shard, lo, hi, st, acc);
+    if (lane == 0) {
+        sup_end[w * nbr + k] = st;
+        sup_acc[(w * nbr + k) * 3 + 0] = acc[0];
+        sup_acc[(w * nbr + k) * 3 + 1] = acc[1];
+        sup_acc[(w * nbr + k) * 3 + 2] = acc[2];
     }
 }
 
-// pass 3: out[i] = candidate[src][i] (segments the resolver wrote itself are left alone)
-__global__ void k_cs_assemble(const float* __restrict__ cand, int64_t n, const uint8_t* __restrict__ src, float* __restrict__ out) {
+// pass 2b: hop over the super-chunks with the TRUE state.  chosen[w] = table family whose entries are right for super-chunk w.
+template <int DT>
+__global__ void __launch_bounds__(32) k_cs_stitch(const void* __restrict__ iq, int64_t n, CsParams P, int64_t nchunks, int nbr,
+                                                  const CsState* __restrict__ ckpt, const int* __restrict__ nonnoise,
+                                                  const int* __restrict__ chunk_cnt, CsTables T, int first_shard, int64_t nsuper,
+                                                  const CsState* __restrict__ sup_end, const int64_t* __restrict__ sup_acc,
+                                                  uint8_t* __restrict__ chosen, int64_t* __restrict__ stats, CsState st_in,
+                                                  CsState* __restrict__ st_out) {
+    const int lane = threadIdx.x;
+    int64_t acc[3] = {0, 0, 0};
+    int64_t redone = 0;
+    CsState st = st_in;
+    int64_t w = 0;
+    if (first_shard) {
+        if (lane == 0) chosen[0] = 0;
+        st = sup_end[0];
+        for (int q = 0; q < 3; q++) acc[q] += sup_acc[q];
+        w = 1;
+    }
+    for (; w < nsuper; w++) {
+        const int64_t lo = w * CS_SUP;
+        int m = -1;
+        if (lane < nbr) {
+            const CsState q = ckpt[((int64_t)lane * nchunks + lo) * (P.segs + 1)];
+            if (__float_as_uint(q.freq) == __float_as_uint(st.freq) && __float_as_uint(q.phase) == __float_as_uint(st.phase)) m = lane;
+        }
+        const unsigned any = __ballot_sync(URH_FULL_MASK, m >= 0);
+        if (any) {
+            const int k = __ffs(any) - 1;
+            if (lane == 0) chosen[w] = (uint8_t)k;
+            st = sup_end[w * nbr + k];
+            for (int q = 0; q < 3; q++) acc[q] += sup_acc[(w * nbr + k) * 3 + q];
+        } else {
+            if (lane == 0) chosen[w] = (uint8_t)nbr;
+            redone++;
+            st = cs_chain<DT>(iq, n, P, nchunks, nbr, ckpt, nonnoise, chunk_cnt, T.src + (int64_t)nbr * T.nseg, T.segst + (int64_t)nbr * T.nseg,
+                              first_shard, lo, min(nchunks, lo + CS_SUP), st, acc);
+        }
+    }
+    if (lane == 0 && st_out) *st_out = st;
+    if (lane == 0 && stats) {
+        stats[0] = acc[0];
+        stats[1] = acc[1];
+        stats[2] = acc[2];
+        stats[3] = redone;
+    }
+}
+
+// pass 3: out[i] = candidate[src][i] (stepped segments are written by k_cs_fix)
+__global__ void k_cs_assemble(const float* __restrict__ cand, int64_t n, CsTables T, int segs, const uint8_t* __restrict__ chosen,
+                              float* __restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint8_t k = src[i / CS_SEG];
+        const int64_t seg = i / CS_SEG;
+        const int64_t w = seg / ((int64_t)segs * CS_SUP);
+        const uint8_t k = T.src[(int64_t)chosen[w] * T.nseg + seg];
         if (k != 255) out[i] = cand[(int64_t)k * n + i];
+    }
+}
+
+// pass 4: the stepped segments (one warp each): recompute the samples from the recorded state
+template <int DT>
+__global__ void __launch_bounds__(128) k_cs_fix(const void* __restrict__ iq, int64_t n, CsParams P, CsTables T, const uint8_t* __restrict__ chosen,
+                                               int first_shard, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < T.nseg; seg += nw) {
+        const int64_t w = seg / ((int64_t)P.segs * CS_SUP);
+        const int64_t t = chosen[w];
+        if (T.src[t * T.nseg + seg] != 255) continue;
+        CsState st = T.segst[t * T.nseg + seg];
+        const int64_t a = seg * CS_SEG;
+        for (int g = 0; g < CS_SEG / 32; g++) {
+            const int64_t i = a + g * 32 + lane;
+            float re = 0.f, im = 0.f;
+            bool live = false;
+            if (i < n && !(i == 0 && first_shard)) {
+                cs_load<DT>(iq, i, re, im);
+                live = !(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)) <= P.noise_sqrd);
+                if (!live) out[i] = -4.0f;
+            } else if (i == 0 && first_shard) {
+                out[0] = 0.0f;
+            }
+            unsigned mask = __ballot_sync(URH_FULL_MASK, live);
+            while (mask) {
+                const int l = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float r1 = __shfl_sync(URH_FULL_MASK, re, l), i1 = __shfl_sync(URH_FULL_MASK, im, l);
+                if (lane == 0) {
+                    float o;
+                    cs_step(st, r1, i1, P, o);
+                    out[a + g * 32 + l] = o;
+                }
+            }
+        }
     }
 }
 
@@ -320,11 +463,24 @@ struct CsRun {
     CsState* ckpt;
     int* nonnoise;
     int* chunk_cnt;
-    uint8_t* src;
+    CsTables T;
+    int64_t nsuper;
+    CsState* sup_end;
+    int64_t* sup_acc;
+    uint8_t* chosen;
     int64_t* stats;
     CsState* st_out;
     float* out;
 };
+
+#define CS_DISPATCH(R, KERNEL, ...)                                                    \
+    switch ((R).dtype) {                                                               \
+        case URH_DT_I8: URH_LAUNCH(ctx, KERNEL<URH_DT_I8>, __VA_ARGS__); break;        \
+        case URH_DT_U8: URH_LAUNCH(ctx, KERNEL<URH_DT_U8>, __VA_ARGS__); break;        \
+        case URH_DT_I16: URH_LAUNCH(ctx, KERNEL<URH_DT_I16>, __VA_ARGS__); break;      \
+        case URH_DT_U16: URH_LAUNCH(ctx, KERNEL<URH_DT_U16>, __VA_ARGS__); break;      \
+        default: URH_LAUNCH(ctx, KERNEL<URH_DT_F32>, __VA_ARGS__); break;              \
+    }
 
 static int cs_speculate(urh_ctx* ctx, CsRun& R) {
     urh_arena_reset(ctx);
@@ -338,32 +494,36 @@ static int cs_speculate(urh_ctx* ctx, CsRun& R) {
     URH_CHECK(urh_arena(ctx, (size_t)R.nbr * R.n, &R.cand));
     URH_CHECK(urh_arena(ctx, (size_t)R.nbr * R.nchunks * (R.P.segs + 1), &R.ckpt));
     URH_CHECK(urh_arena(ctx, (size_t)R.nchunks * R.P.segs, &R.nonnoise));
-    URH_CHECK(urh_arena(ctx, (size_t)R.nchunks * R.P.segs, &R.src));
+    R.T.nseg = R.nchunks * R.P.segs;
+    R.nsuper = urh_div_up(R.nchunks, CS_SUP);
+    URH_CHECK(urh_arena(ctx, (size_t)(R.nbr + 1) * R.T.nseg, &R.T.src));
+    URH_CHECK(urh_arena(ctx, (size_t)(R.nbr + 1) * R.T.nseg, &R.T.segst));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nsuper * R.nbr, &R.sup_end));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nsuper * R.nbr * 3, &R.sup_acc));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nsuper, &R.chosen));
     URH_CHECK(urh_arena(ctx, (size_t)R.nchunks, &R.chunk_cnt));
     URH_CHECK(urh_arena(ctx, 4, &R.stats));
     URH_CHECK(urh_arena(ctx, 2, &R.st_out));
     const dim3 grid((unsigned)urh_div_up(R.nchunks, 128), (unsigned)R.nbr);
-    switch (R.dtype) {
-        case URH_DT_I8: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_I8>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard); break;
-        case URH_DT_U8: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_U8>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard); break;
-        case URH_DT_I16: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_I16>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard); break;
-        case URH_DT_U16: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_U16>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard); break;
-        default: URH_LAUNCH(ctx, k_cs_speculate<URH_DT_F32>, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard); break;
-    }
+    CS_DISPATCH(R, k_cs_speculate, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard);
+    // pass 2a: the chains of every super-chunk under every assumption (independent of the true incoming state)
+    URH_CUDA(ctx, cudaMemsetAsync(R.sup_acc, 0, (size_t)R.nsuper * R.nbr * 3 * sizeof(int64_t), ctx->stream));
+    CS_DISPATCH(R, k_cs_chains, (unsigned)urh_div_up(R.nsuper * R.nbr * 32, 128), 128, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise,
+                R.chunk_cnt, R.T, R.first_shard, R.nsuper, R.sup_end, R.sup_acc);
     return URH_OK;
 }
 
 static int cs_resolve(urh_ctx* ctx, CsRun& R, CsState st_in, float* h_state_out) {
-    switch (R.dtype) {
-        case URH_DT_I8: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_I8>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
-        case URH_DT_U8: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_U8>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
-        case URH_DT_I16: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_I16>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
-        case URH_DT_U16: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_U16>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
-        default: URH_LAUNCH(ctx, k_cs_resolve<URH_DT_F32>, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.out, R.src, R.stats, R.first_shard, st_in, R.st_out); break;
-    }
+    CS_DISPATCH(R, k_cs_stitch, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.T, R.first_shard, R.nsuper,
+                R.sup_end, R.sup_acc, R.chosen, R.stats, st_in, R.st_out);
     const unsigned ga = (unsigned)min(urh_div_up(R.n, 256), (int64_t)ctx->sm_count * 32);
-    URH_LAUNCH(ctx, k_cs_assemble, ga, 256, 0, R.cand, R.n, R.src, R.out);
-    URH_CHECK(urh_read_i64(ctx, R.stats, 3, ctx->costas_stats));
+    URH_LAUNCH(ctx, k_cs_assemble, ga, 256, 0, R.cand, R.n, R.T, R.P.segs, R.chosen, R.out);
+    CS_DISPATCH(R, k_cs_fix, (unsigned)min(urh_div_up(R.T.nseg * 32, 128), (int64_t)ctx->sm_count * 16), 128, 0, R.iq, R.n, R.P, R.T, R.chosen,
+                R.first_shard, R.out);
+    int64_t st4[4];
+    URH_CHECK(urh_read_i64(ctx, R.stats, 4, st4));
+    for (int i = 0; i < 3; i++) ctx->costas_stats[i] = st4[i];
+    ctx->costas_redone = st4[3];
     if (h_state_out) {
         URH_CUDA(ctx, cudaMemcpyAsync(h_state_out, R.st_out, sizeof(CsState), cudaMemcpyDeviceToHost, ctx->stream));
         URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -417,3 +577,6 @@ extern "C" int urh_costas_stats(urh_ctx* ctx, int64_t* h_out3) {
     for (int i = 0; i < 3; i++) h_out3[i] = ctx->costas_stats[i];
     return URH_OK;
 }
+
+// super-chunks whose chain the stitch pass had to run itself in the last speculative run (no assumption matched)
+extern "C" int64_t urh_costas_last_redone(urh_ctx* ctx) { return ctx->costas_redone; }
