@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ i
 #define CS_SUP 64
 
 struct CsTables {
-    uint8_t* src;     // [nbr + 1][nseg]
-    CsState* segst;   // [nbr + 1][nseg]
+    uint8_t* src;     // [2 * nbr + 1][nseg]
+    CsState* segst;   // [2 * nbr + 1][nseg]
     int64_t nseg;     // nchunks * segs
 };
 
@@ -297,10 +297,15 @@ __device__ CsState cs_chain(const void* __restrict__ iq, int64_t n, const CsPara
 }
 
 // pass 2a: one warp per (super-chunk w, assumption k).  sup_end[w*nbr + k] = state after the super-chunk, sup_acc its counters.
+// family 0 ("A"): the super-chunk starts in candidate k's start state (right whenever the loop is locked at its first sample).
+// family 1 ("B"): it starts in the state family-A chain k of the last super-chunk WITH SIGNAL before it ended in -- right
+//                 when the super-chunk starts inside a gap: the loop state is frozen there (or creeps on noise spikes), no
+//                 candidate warm-up can reproduce it, but it is what the previous burst left behind.
 template <int DT>
 __global__ void __launch_bounds__(128) k_cs_chains(const void* __restrict__ iq, int64_t n, CsParams P, int64_t nchunks, int nbr,
                                                   const CsState* __restrict__ ckpt, const int* __restrict__ nonnoise,
                                                   const int* __restrict__ chunk_cnt, CsTables T, int first_shard, int64_t nsuper,
+                                                  int family, const int64_t* __restrict__ prev_live, const CsState* __restrict__ end_a,
                                                   CsState* __restrict__ sup_end, int64_t* __restrict__ sup_acc) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -311,16 +316,28 @@ __global__ void __launch_bounds__(128) k_cs_chains(const void* __restrict__ iq, 
     const int64_t hi = min(nchunks, lo + CS_SUP);
     int64_t acc[3] = {0, 0, 0};
     CsState st;
-    uint8_t* src = T.src + (int64_t)k * T.nseg;
-    CsState* segst = T.segst + (int64_t)k * T.nseg;
-    if (w == 0 && first_shard) {
-        // the capture's first chunk is the one exact run (candidate 0 started from the loop's true initial state)
-        if (k != 0) return;
-        if (lane < P.segs) src[lane] = 0;
-        st = ckpt[P.segs];
-        lo = 1;
+    uint8_t* src = T.src + (int64_t)(family * nbr + k) * T.nseg;
+    CsState* segst = T.segst + (int64_t)(family * nbr + k) * T.nseg;
+    if (family == 0) {
+        if (w == 0 && first_shard) {
+            // the capture's first chunk is the one exact run (candidate 0 started from the loop's true initial state)
+            if (k != 0) {
+                if (lane == 0) sup_end[w * nbr + k].freq = sup_end[w * nbr + k].phase = __int_as_float(0x7fc00000);
+                return;
+            }
+            if (lane < P.segs) src[lane] = 0;
+            st = ckpt[P.segs];
+            lo = 1;
+        } else {
+            st = ckpt[((int64_t)k * nchunks + lo) * (P.segs + 1)];
+        }
     } else {
-        st = ckpt[((int64_t)k * nchunks + lo) * (P.segs + 1)];
+        const int64_t p = prev_live[w];
+        if (p < 0 || (p == 0 && first_shard && k != 0)) {   // nothing to inherit (family A of super-chunk 0 has one chain only)
+            if (lane == 0) sup_end[w * nbr + k].freq = sup_end[w * nbr + k].phase = __int_as_float(0x7fc00000);
+            return;
+        }
+        st = end_a[p * nbr + k];
     }
     st = cs_chain<DT>(iq, n, P, nchunks, nbr, ckpt, nonnoise, chunk_cnt, src, segst, first_shard, lo, hi, st, acc);
     if (lane == 0) {
@@ -331,14 +348,33 @@ __global__ void __launch_bounds__(128) k_cs_chains(const void* __restrict__ iq, 
     }
 }
 
-// pass 2b: hop over the super-chunks with the TRUE state.  chosen[w] = table family whose entries are right for super-chunk w.
+// prev_live[w] = last super-chunk before w that holds at least one sample above the noise gate (-1: none)
+__global__ void k_cs_live(const int* __restrict__ chunk_cnt, int64_t nchunks, int64_t nsuper, int64_t* __restrict__ live) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nsuper) return;
+    int64_t any = 0;
+    for (int64_t c = w * CS_SUP; c < min(nchunks, (w + 1) * CS_SUP); c++) any |= chunk_cnt[c] > 0 ? 1 : 0;
+    live[w] = any;
+}
+__global__ void k_cs_prev_live(const int64_t* __restrict__ live, int64_t nsuper, int64_t* __restrict__ prev_live) {
+    if (blockIdx.x || threadIdx.x) return;
+    int64_t last = -1;
+    for (int64_t w = 0; w < nsuper; w++) {
+        prev_live[w] = last;
+        if (live[w]) last = w;
+    }
+}
+
+// pass 2b: hop over the super-chunks with the TRUE state.  chosen[w] = table family whose entries are right for super-chunk w
+// (k: family A chain k, nbr + k: family B chain k, 2*nbr: the chain this kernel ran itself).
 template <int DT>
 __global__ void __launch_bounds__(32) k_cs_stitch(const void* __restrict__ iq, int64_t n, CsParams P, int64_t nchunks, int nbr,
                                                   const CsState* __restrict__ ckpt, const int* __restrict__ nonnoise,
                                                   const int* __restrict__ chunk_cnt, CsTables T, int first_shard, int64_t nsuper,
-                                                  const CsState* __restrict__ sup_end, const int64_t* __restrict__ sup_acc,
-                                                  uint8_t* __restrict__ chosen, int64_t* __restrict__ stats, CsState st_in,
-                                                  CsState* __restrict__ st_out) {
+                                                  const int64_t* __restrict__ prev_live, const CsState* __restrict__ end_a,
+                                                  const CsState* __restrict__ end_b, const int64_t* __restrict__ acc_a,
+                                                  const int64_t* __restrict__ acc_b, uint8_t* __restrict__ chosen,
+                                                  int64_t* __restrict__ stats, CsState st_in, CsState* __restrict__ st_out) {
     const int lane = threadIdx.x;
     int64_t acc[3] = {0, 0, 0};
     int64_t redone = 0;
@@ -346,28 +382,42 @@ __global__ void __launch_bounds__(32) k_cs_stitch(const void* __restrict__ iq, i
     int64_t w = 0;
     if (first_shard) {
         if (lane == 0) chosen[0] = 0;
-        st = sup_end[0];
-        for (int q = 0; q < 3; q++) acc[q] += sup_acc[q];
+        st = end_a[0];
+        for (int q = 0; q < 3; q++) acc[q] += acc_a[q];
         w = 1;
     }
     for (; w < nsuper; w++) {
         const int64_t lo = w * CS_SUP;
+        const int64_t p = prev_live[w];
+        // lanes 0..nbr-1: family A start states (candidate checkpoints); lanes 8..8+nbr-1: family B start states
         int m = -1;
         if (lane < nbr) {
             const CsState q = ckpt[((int64_t)lane * nchunks + lo) * (P.segs + 1)];
             if (__float_as_uint(q.freq) == __float_as_uint(st.freq) && __float_as_uint(q.phase) == __float_as_uint(st.phase)) m = lane;
+        } else if (lane >= 8 && lane < 8 + nbr && p >= 0) {
+            const int k = lane - 8;
+            const CsState q = end_a[p * nbr + k];
+            const CsState e = end_b[w * nbr + k];
+            if (__float_as_uint(q.freq) == __float_as_uint(st.freq) && __float_as_uint(q.phase) == __float_as_uint(st.phase) &&
+                e.freq == e.freq)   // NaN end state = chain B k was not run
+                m = lane;
         }
         const unsigned any = __ballot_sync(URH_FULL_MASK, m >= 0);
-        if (any) {
-            const int k = __ffs(any) - 1;
+        if (any & 0xffu) {
+            const int k = __ffs(any & 0xffu) - 1;
             if (lane == 0) chosen[w] = (uint8_t)k;
-            st = sup_end[w * nbr + k];
-            for (int q = 0; q < 3; q++) acc[q] += sup_acc[(w * nbr + k) * 3 + q];
+            st = end_a[w * nbr + k];
+            for (int q = 0; q < 3; q++) acc[q] += acc_a[(w * nbr + k) * 3 + q];
+        } else if (any) {
+            const int k = __ffs(any) - 1 - 8;
+            if (lane == 0) chosen[w] = (uint8_t)(nbr + k);
+            st = end_b[w * nbr + k];
+            for (int q = 0; q < 3; q++) acc[q] += acc_b[(w * nbr + k) * 3 + q];
         } else {
-            if (lane == 0) chosen[w] = (uint8_t)nbr;
+            if (lane == 0) chosen[w] = (uint8_t)(2 * nbr);
             redone++;
-            st = cs_chain<DT>(iq, n, P, nchunks, nbr, ckpt, nonnoise, chunk_cnt, T.src + (int64_t)nbr * T.nseg, T.segst + (int64_t)nbr * T.nseg,
-                              first_shard, lo, min(nchunks, lo + CS_SUP), st, acc);
+            st = cs_chain<DT>(iq, n, P, nchunks, nbr, ckpt, nonnoise, chunk_cnt, T.src + (int64_t)(2 * nbr) * T.nseg,
+                              T.segst + (int64_t)(2 * nbr) * T.nseg, first_shard, lo, min(nchunks, lo + CS_SUP), st, acc);
         }
     }
     if (lane == 0 && st_out) *st_out = st;
@@ -465,8 +515,10 @@ struct CsRun {
     int* chunk_cnt;
     CsTables T;
     int64_t nsuper;
-    CsState* sup_end;
-    int64_t* sup_acc;
+    CsState* sup_end;   // [2][nsuper * nbr]: family A, family B
+    int64_t* sup_acc;   // [2][nsuper * nbr * 3]
+    int64_t* live;      // [nsuper]
+    int64_t* prev_live; // [nsuper]
     uint8_t* chosen;
     int64_t* stats;
     CsState* st_out;
@@ -496,10 +548,12 @@ static int cs_speculate(urh_ctx* ctx, CsRun& R) {
     URH_CHECK(urh_arena(ctx, (size_t)R.nchunks * R.P.segs, &R.nonnoise));
     R.T.nseg = R.nchunks * R.P.segs;
     R.nsuper = urh_div_up(R.nchunks, CS_SUP);
-    URH_CHECK(urh_arena(ctx, (size_t)(R.nbr + 1) * R.T.nseg, &R.T.src));
-    URH_CHECK(urh_arena(ctx, (size_t)(R.nbr + 1) * R.T.nseg, &R.T.segst));
-    URH_CHECK(urh_arena(ctx, (size_t)R.nsuper * R.nbr, &R.sup_end));
-    URH_CHECK(urh_arena(ctx, (size_t)R.nsuper * R.nbr * 3, &R.sup_acc));
+    URH_CHECK(urh_arena(ctx, (size_t)(2 * R.nbr + 1) * R.T.nseg, &R.T.src));
+    URH_CHECK(urh_arena(ctx, (size_t)(2 * R.nbr + 1) * R.T.nseg, &R.T.segst));
+    URH_CHECK(urh_arena(ctx, (size_t)2 * R.nsuper * R.nbr, &R.sup_end));
+    URH_CHECK(urh_arena(ctx, (size_t)2 * R.nsuper * R.nbr * 3, &R.sup_acc));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nsuper, &R.live));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nsuper, &R.prev_live));
     URH_CHECK(urh_arena(ctx, (size_t)R.nsuper, &R.chosen));
     URH_CHECK(urh_arena(ctx, (size_t)R.nchunks, &R.chunk_cnt));
     URH_CHECK(urh_arena(ctx, 4, &R.stats));
@@ -507,15 +561,23 @@ static int cs_speculate(urh_ctx* ctx, CsRun& R) {
     const dim3 grid((unsigned)urh_div_up(R.nchunks, 128), (unsigned)R.nbr);
     CS_DISPATCH(R, k_cs_speculate, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard);
     // pass 2a: the chains of every super-chunk under every assumption (independent of the true incoming state)
-    URH_CUDA(ctx, cudaMemsetAsync(R.sup_acc, 0, (size_t)R.nsuper * R.nbr * 3 * sizeof(int64_t), ctx->stream));
-    CS_DISPATCH(R, k_cs_chains, (unsigned)urh_div_up(R.nsuper * R.nbr * 32, 128), 128, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise,
-                R.chunk_cnt, R.T, R.first_shard, R.nsuper, R.sup_end, R.sup_acc);
+    const int64_t per = R.nsuper * R.nbr;
+    URH_CUDA(ctx, cudaMemsetAsync(R.sup_acc, 0, (size_t)2 * per * 3 * sizeof(int64_t), ctx->stream));
+    URH_LAUNCH(ctx, k_cs_live, (unsigned)urh_div_up(R.nsuper, 128), 128, 0, R.chunk_cnt, R.nchunks, R.nsuper, R.live);
+    URH_LAUNCH(ctx, k_cs_prev_live, 1, 32, 0, (const int64_t*)R.live, R.nsuper, R.prev_live);
+    const unsigned gc = (unsigned)urh_div_up(per * 32, 128);
+    CS_DISPATCH(R, k_cs_chains, gc, 128, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.T, R.first_shard, R.nsuper, 0,
+                (const int64_t*)R.prev_live, (const CsState*)R.sup_end, R.sup_end, R.sup_acc);
+    CS_DISPATCH(R, k_cs_chains, gc, 128, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.T, R.first_shard, R.nsuper, 1,
+                (const int64_t*)R.prev_live, (const CsState*)R.sup_end, R.sup_end + per, R.sup_acc + per * 3);
     return URH_OK;
 }
 
 static int cs_resolve(urh_ctx* ctx, CsRun& R, CsState st_in, float* h_state_out) {
+    const int64_t per = R.nsuper * R.nbr;
     CS_DISPATCH(R, k_cs_stitch, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.T, R.first_shard, R.nsuper,
-                R.sup_end, R.sup_acc, R.chosen, R.stats, st_in, R.st_out);
+                (const int64_t*)R.prev_live, (const CsState*)R.sup_end, (const CsState*)(R.sup_end + per), (const int64_t*)R.sup_acc,
+                (const int64_t*)(R.sup_acc + per * 3), R.chosen, R.stats, st_in, R.st_out);
     const unsigned ga = (unsigned)min(urh_div_up(R.n, 256), (int64_t)ctx->sm_count * 32);
     URH_LAUNCH(ctx, k_cs_assemble, ga, 256, 0, R.cand, R.n, R.T, R.P.segs, R.chosen, R.out);
     CS_DISPATCH(R, k_cs_fix, (unsigned)min(urh_div_up(R.T.nseg * 32, 128), (int64_t)ctx->sm_count * 16), 128, 0, R.iq, R.n, R.P, R.T, R.chosen,
