@@ -175,6 +175,9 @@ int urh_costas_halo_samples(void);
 int urh_costas_shard_speculate(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int first_shard, float noise_mag,
                                int loop_order, float bandwidth, float* d_out);
 int urh_costas_shard_resolve(urh_ctx* ctx, const float* h_state_in, float* h_state_out);
+/* replaces the arithmetic of IQArray.convert_to (IQArray.py:127-200): capture formats cs8/cu8/cs16/cu16/float32 into each
+ * other (numpy's integer wrap-around, C truncation for float -> int).  count = number of elements (2 per sample). */
+int urh_convert_iq(urh_ctx* ctx, const void* d_in, int in_dtype, void* d_out, int out_dtype, int64_t count);
 /* the sample-rate part of AutoInterpretation.detect_modulation (AutoInterpretation.py:151-208) for one message
  * (d_data = complex64[n] on the device): zero removal, normalisation, the two Haar wavelet transforms (cuFFT for the FFTs),
  * variances before/after the median filter and the spectrum features of the FSK test.  h_feat[8] = {n_nonzero, P, L, var_mag,

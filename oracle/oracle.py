@@ -385,3 +385,62 @@ def detect_modulation(data, wavelet_scale=4, median_filter_order=11):
     if var_mag > 10 * var_filtered_mag:
         return "PSK"
     return "FSK" if fsk else "OOK"
+
+
+# ---- capture format conversion (IQArray.py:127-200) ------------------------------------------------------------------
+def convert_iq(data, target_dtype):
+    """IQArray.convert_to (IQArray.py:127-200) restated with the same numpy operations"""
+    _INT_TYPES = (np.uint8, np.int8, np.uint16, np.int16)
+    src = data.dtype
+    tgt = np.dtype(target_dtype)
+    d = data
+    if tgt == src:
+        return d
+    if tgt not in [np.dtype(t) for t in _INT_TYPES + (np.float32,)]:
+        raise ValueError("Data type {} not supported".format(target_dtype))
+    if src == np.uint8:
+        if tgt == np.int8:
+            return np.add(d, -128, dtype=np.int8, casting="unsafe")
+        if tgt == np.int16:
+            return np.add(d, -128, dtype=np.int16, casting="unsafe") << 8
+        if tgt == np.uint16:
+            return d.astype(np.uint16) << 8
+        if tgt == np.float32:
+            return np.add(np.multiply(d, 1 / 128, dtype=np.float32), -1.0, dtype=np.float32)
+    if src == np.int8:
+        if tgt == np.uint8:
+            return np.add(d, 128, dtype=np.uint8, casting="unsafe")
+        if tgt == np.int16:
+            return d.astype(np.int16) << 8
+        if tgt == np.uint16:
+            return np.add(d, 128, dtype=np.uint16, casting="unsafe") << 8
+        if tgt == np.float32:
+            return np.multiply(d, 1 / 128, dtype=np.float32)
+    if src == np.uint16:
+        if tgt == np.int8:
+            return (np.add(d, -32768, dtype=np.int16, casting="unsafe") >> 8).astype(np.int8)
+        if tgt == np.uint8:
+            return (d >> 8).astype(np.uint8)
+        if tgt == np.int16:
+            return np.add(d, -32768, dtype=np.int16, casting="unsafe")
+        if tgt == np.float32:
+            return np.add(np.multiply(d, 1 / 32768, dtype=np.float32), -1.0, dtype=np.float32)
+    if src == np.int16:
+        if tgt == np.int8:
+            return (d >> 8).astype(np.int8)
+        if tgt == np.uint8:
+            return (np.add(d, 32768, dtype=np.uint16, casting="unsafe") >> 8).astype(np.uint8)
+        if tgt == np.uint16:
+            return np.add(d, 32768, dtype=np.uint16, casting="unsafe")
+        if tgt == np.float32:
+            return np.multiply(d, 1 / 32768, dtype=np.float32)
+    if src == np.float32:
+        if tgt == np.int8:
+            return np.multiply(d, 127, dtype=np.float32).astype(np.int8)
+        if tgt == np.uint8:
+            return np.multiply(np.add(d, 1.0, dtype=np.float32), 127, dtype=np.float32).astype(np.uint8)
+        if tgt == np.int16:
+            return np.multiply(d, 32767, dtype=np.float32).astype(np.int16)
+        if tgt == np.uint16:
+            return np.multiply(np.add(d, 1.0, dtype=np.float32), 32767, dtype=np.float32).astype(np.uint16)
+    raise NotImplementedError("Conversion from {} to {} not supported", src, tgt)

@@ -273,3 +273,21 @@ def test_signal_auto_detect_and_edit(sp):
     assert s._qad is None and s.qad.shape == q0.shape
     thr = s.get_thresholds_for_center(0.5)
     assert thr.dtype == np.float32 and len(thr) == 1
+
+
+# ---- capture format conversions on the device (convert.cu) vs the oracle's numpy restatement of IQArray.convert_to -------
+@pytest.mark.parametrize("src", [np.int8, np.uint8, np.int16, np.uint16, np.float32])
+@pytest.mark.parametrize("dst", [np.int8, np.uint8, np.int16, np.uint16, np.float32])
+def test_convert_to_all_pairs(oracle, src, dst):
+    from urh_b200.signalprocessing.IQArray import IQArray
+    rng = np.random.default_rng(5)
+    if src == np.float32:
+        x = np.concatenate([rng.uniform(-1, 1, 4000), [-1.0, 1.0, 0.0, -0.0, 0.999999, -0.999999, 0.5, -0.5]]).astype(np.float32)
+    else:
+        info = np.iinfo(src)
+        x = np.concatenate([rng.integers(info.min, info.max + 1, 4000), [info.min, info.max, 0, 1, info.max - 1, info.min + 1, 2, 3]]).astype(src)
+    x = np.ascontiguousarray(x.reshape(-1, 2))
+    got = IQArray(x).convert_to(dst)
+    ref = oracle.convert_iq(x, dst)
+    assert got.dtype == ref.dtype and got.shape == ref.shape
+    assert np.array_equal(got.view(np.uint8), ref.view(np.uint8)), (src, dst)

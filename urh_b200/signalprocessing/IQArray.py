@@ -132,59 +132,30 @@ class IQArray(object):
 
     # -- dtype conversion (IQArray.py:129-203) -------------------------------------------------------------------------
     def convert_to(self, target_dtype) -> np.ndarray:
-        src = self.__data.dtype
+        """IQArray.py:127-200.  The element-wise conversion runs on the GPU (convert.cu); the same object is returned when
+        the dtype already matches."""
         tgt = np.dtype(target_dtype)
-        d = self.__data
-        if tgt == src:
-            return d
+        if tgt == self.__data.dtype:
+            return self.__data
         if tgt not in [np.dtype(t) for t in _INT_TYPES + (np.float32,)]:
             raise ValueError("Data type {} not supported".format(target_dtype))
-        if src == np.uint8:
-            if tgt == np.int8:
-                return np.add(d, -128, dtype=np.int8, casting="unsafe")
-            if tgt == np.int16:
-                return np.add(d, -128, dtype=np.int16, casting="unsafe") << 8
-            if tgt == np.uint16:
-                return d.astype(np.uint16) << 8
-            if tgt == np.float32:
-                return np.add(np.multiply(d, 1 / 128, dtype=np.float32), -1.0, dtype=np.float32)
-        if src == np.int8:
-            if tgt == np.uint8:
-                return np.add(d, 128, dtype=np.uint8, casting="unsafe")
-            if tgt == np.int16:
-                return d.astype(np.int16) << 8
-            if tgt == np.uint16:
-                return np.add(d, 128, dtype=np.uint16, casting="unsafe") << 8
-            if tgt == np.float32:
-                return np.multiply(d, 1 / 128, dtype=np.float32)
-        if src == np.uint16:
-            if tgt == np.int8:
-                return (np.add(d, -32768, dtype=np.int16, casting="unsafe") >> 8).astype(np.int8)
-            if tgt == np.uint8:
-                return (d >> 8).astype(np.uint8)
-            if tgt == np.int16:
-                return np.add(d, -32768, dtype=np.int16, casting="unsafe")
-            if tgt == np.float32:
-                return np.add(np.multiply(d, 1 / 32768, dtype=np.float32), -1.0, dtype=np.float32)
-        if src == np.int16:
-            if tgt == np.int8:
-                return (d >> 8).astype(np.int8)
-            if tgt == np.uint8:
-                return (np.add(d, 32768, dtype=np.uint16, casting="unsafe") >> 8).astype(np.uint8)
-            if tgt == np.uint16:
-                return np.add(d, 32768, dtype=np.uint16, casting="unsafe")
-            if tgt == np.float32:
-                return np.multiply(d, 1 / 32768, dtype=np.float32)
-        if src == np.float32:
-            if tgt == np.int8:
-                return np.multiply(d, 127, dtype=np.float32).astype(np.int8)
-            if tgt == np.uint8:
-                return np.multiply(np.add(d, 1.0, dtype=np.float32), 127, dtype=np.float32).astype(np.uint8)
-            if tgt == np.int16:
-                return np.multiply(d, 32767, dtype=np.float32).astype(np.int16)
-            if tgt == np.uint16:
-                return np.multiply(np.add(d, 1.0, dtype=np.float32), 32767, dtype=np.float32).astype(np.uint16)
-        raise NotImplementedError("Conversion from {} to {} not supported", src, tgt)
+        return self.convert_to_device(tgt).get()
+
+    def convert_to_device(self, target_dtype):
+        """the converted capture as a DeviceArray (no download)"""
+        import ctypes as C
+
+        from .. import _lib
+        from ..device import DeviceArray
+
+        tgt = np.dtype(target_dtype)
+        src = self.device()
+        if tgt == src.dtype:
+            return src
+        out = DeviceArray(src.ctx, self.__data.shape, tgt)
+        src.ctx.check(src.ctx.lib.urh_convert_iq(src.ctx.handle, C.c_void_p(src.ptr), _lib.dtype_code(src.dtype), C.c_void_p(out.ptr),
+                                                  _lib.dtype_code(tgt), int(self.__data.size)))
+        return out
 
     # -- files (IQArray.py:115-127, 205-227, 263-275) -------------------------------------------------------------------
     _EXT = {
