@@ -175,6 +175,8 @@ int urh_costas_halo_samples(void);
 int urh_costas_shard_speculate(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int first_shard, float noise_mag,
                                int loop_order, float bandwidth, float* d_out);
 int urh_costas_shard_resolve(urh_ctx* ctx, const float* h_state_in, float* h_state_out);
+/* Signal.estimate_frequency (Signal.py:578-601): arg-max bin of fft(x[0:P]), P = 2^floor(log2 n) (complex64 on the device) */
+int urh_fft_argmax(urh_ctx* ctx, const float* d_x, int64_t n, int64_t* h_index, int64_t* h_P);
 /* replaces the arithmetic of IQArray.convert_to (IQArray.py:127-200): capture formats cs8/cu8/cs16/cu16/float32 into each
  * other (numpy's integer wrap-around, C truncation for float -> int).  count = number of elements (2 per sample). */
 int urh_convert_iq(urh_ctx* ctx, const void* d_in, int in_dtype, void* d_out, int out_dtype, int64_t count);

@@ -291,3 +291,25 @@ def test_convert_to_all_pairs(oracle, src, dst):
     ref = oracle.convert_iq(x, dst)
     assert got.dtype == ref.dtype and got.shape == ref.shape
     assert np.array_equal(got.view(np.uint8), ref.view(np.uint8)), (src, dst)
+
+
+def test_estimate_frequency_matches_numpy():
+    """Signal.estimate_frequency (device FFT arg-max) == the reference's numpy formula on golden captures and tones"""
+    from urh_b200.signalprocessing.IQArray import IQArray
+    from urh_b200.signalprocessing.Signal import Signal
+    for name, (start, end) in (("fsk", (100, 17000)), ("ask", (462, 754)), ("homematic", (17718, 37862))):
+        g = load_golden("capture_" + name)
+        s = Signal("", "t")
+        s.iq_array = IQArray(g["iq"])
+        length = 2 ** int(np.log2(end - start))
+        data = s.iq_array.as_complex64()[start:start + length]
+        w = np.fft.fft(data)
+        ref = abs(np.fft.fftfreq(len(w))[np.argmax(np.abs(w))] * 1e6)
+        assert s.estimate_frequency(start, end, 1e6) == ref, name
+    t = np.arange(5000)
+    for f in (0.01, -0.2, 0.4999, 0.0):
+        x = np.exp(2j * np.pi * f * t).astype(np.complex64)
+        s = Signal("", "t")
+        s.iq_array = IQArray(x)
+        w = np.fft.fft(x[:4096])
+        assert s.estimate_frequency(0, 5000, 2e6) == abs(np.fft.fftfreq(4096)[np.argmax(np.abs(w))] * 2e6)

@@ -106,6 +106,7 @@ SIGNATURES = {
     "urh_costas_halo_samples": (i32, []),
     "urh_costas_shard_speculate": (i32, [vp, vp, i32, i64, i32, f32, i32, f32, vp]),
     "urh_costas_shard_resolve": (i32, [vp, vp, vp]),
+    "urh_fft_argmax": (i32, [vp, vp, i64, vp, vp]),
     "urh_convert_iq": (i32, [vp, vp, i32, vp, i32, i64]),
     "urh_modulation_features": (i32, [vp, vp, i64, i32, i32, vp, vp]),
     "urh_cwt_haar": (i32, [vp, vp, i32, i64, i32, vp, vp]),

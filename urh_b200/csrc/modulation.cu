@@ -381,3 +381,63 @@ void urh_release_mod_plans(urh_ctx* ctx) {
             ctx->mod_plan_valid[i] = 0;
         }
 }
+
+// arg-max of |fft(x)| (float32 transform and magnitudes, as numpy computes them for complex64 input); first index on ties.
+__global__ void __launch_bounds__(256) k_mod_argmax_first(const float2* __restrict__ xhat, int64_t P, float* __restrict__ pv, int64_t* __restrict__ pi_) {
+    float best = -1.0f;
+    int64_t bi = -1;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < P; i += (int64_t)gridDim.x * 256) {
+        const float2 v = xhat[i];
+        const float a = hypotf(v.x, v.y);
+        if (a > best) { best = a; bi = i; }   // ascending i per thread: keeps the first
+    }
+    __shared__ float sv[256];
+    __shared__ int64_t si[256];
+    sv[threadIdx.x] = best; si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            const float a = sv[threadIdx.x + off];
+            const int64_t b = si[threadIdx.x + off];
+            if (b >= 0 && (a > sv[threadIdx.x] || (a == sv[threadIdx.x] && b < si[threadIdx.x]) || si[threadIdx.x] < 0)) { sv[threadIdx.x] = a; si[threadIdx.x] = b; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { pv[blockIdx.x] = sv[0]; pi_[blockIdx.x] = si[0]; }
+}
+
+// Signal.estimate_frequency (Signal.py:578-601): index of the strongest bin of fft(x[0:P]), P = 2^floor(log2 n).
+// *h_index in [0, P); the caller maps it through np.fft.fftfreq.  *h_P = P (0: n == 0).
+extern "C" int urh_fft_argmax(urh_ctx* ctx, const float* d_x, int64_t n, int64_t* h_index, int64_t* h_P) {
+    if (!h_index || !h_P) return URH_ERR_INVALID;
+    *h_index = 0; *h_P = 0;
+    if (n <= 0) return URH_OK;
+    urh_arena_reset(ctx);
+    int64_t P = 1;
+    while (P * 2 <= n) P *= 2;
+    if (P > ((int64_t)1 << 27)) URH_FAIL(ctx, URH_ERR_INVALID, "window too long for the FFT");
+    float2* xf;
+    double2* unused = nullptr;
+    URH_CHECK(urh_arena(ctx, (size_t)2 * P, &xf));
+    URH_LAUNCH(ctx, k_mod_dup, (unsigned)urh_div_up(P, 256), 256, 0, (const void*)d_x, 0, P, xf, unused);
+    URH_CHECK(mod_plan(ctx, 0, CUFFT_C2C, P));
+    URH_CUFFT(ctx, cufftExecC2C((cufftHandle)ctx->mod_plan[0], (cufftComplex*)xf, (cufftComplex*)xf, CUFFT_FORWARD));
+    const int sb = (int)min((int64_t)ctx->sm_count * 2, urh_div_up(P, 256));
+    float* pv;
+    int64_t* pidx;
+    URH_CHECK(urh_arena(ctx, (size_t)sb, &pv));
+    URH_CHECK(urh_arena(ctx, (size_t)sb, &pidx));
+    URH_LAUNCH(ctx, k_mod_argmax_first, sb, 256, 0, (const float2*)xf, P, pv, pidx);
+    std::vector<float> hv((size_t)sb);
+    std::vector<int64_t> hi((size_t)sb);
+    URH_CUDA(ctx, cudaMemcpyAsync(hv.data(), pv, (size_t)sb * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaMemcpyAsync(hi.data(), pidx, (size_t)sb * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float bv = -1.0f;
+    int64_t bi = -1;
+    for (int b = 0; b < sb; b++)
+        if (hi[b] >= 0 && (hv[b] > bv || (hv[b] == bv && hi[b] < bi) || bi < 0)) { bv = hv[b]; bi = hi[b]; }
+    *h_index = bi < 0 ? 0 : bi;
+    *h_P = P;
+    return URH_OK;
+}

@@ -464,15 +464,26 @@ class Signal(object):
             self.parameter_cache[mod]["center"] = None
 
     def estimate_frequency(self, start: int, end: int, sample_rate: float):
-        """FFT arg-max of a power-of-two window (Signal.py:578-601; row f-4 of the scope table: host numpy)"""
-        try:
-            length = 2 ** int(math.log2(end - start))
-            data = self.iq_array.as_complex64()[start: start + length]
-            w = np.fft.fft(data)
-            freq = np.fft.fftfreq(len(w))[np.argmax(np.abs(w))]
-            return abs(freq * sample_rate)
-        except ValueError:
+        """FFT arg-max of a power-of-two window (Signal.py:578-601); transform and arg-max on the GPU (modulation.cu)"""
+        import ctypes as C
+
+        from .. import _lib
+        from ..device import to_device
+
+        if end - start <= 0:
             return 100e3  # empty window
+        length = 2 ** int(math.log2(end - start))
+        data = np.ascontiguousarray(self.iq_array.as_complex64()[start: start + length])
+        if len(data) == 0:
+            return 100e3
+        ctx = _lib.default_context()
+        d = to_device(data.view(np.float32), ctx)
+        idx, P = C.c_int64(0), C.c_int64(0)
+        ctx.check(ctx.lib.urh_fft_argmax(ctx.handle, C.c_void_p(d.ptr), len(data), C.byref(idx), C.byref(P)))
+        n = P.value
+        k = idx.value
+        freq = (k if k < (n + 1) // 2 else k - n) / n   # np.fft.fftfreq(n)[k]
+        return abs(freq * sample_rate)
 
     def eliminate(self):
         self.iq_array = None
