@@ -123,3 +123,71 @@ def test_sharded_protocol_matches_serial_digitizer_gloo(tmp_path):
     port = 29650 + os.getpid() % 200
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert open(tmp_path / "ok").read() == "1"
+
+
+# ---- capture-wide detect_center over shards: the exchange protocol of urh_b200.dist.center_protocol over gloo -------------
+def _center_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from urh_b200.dist import HostExchange, center_protocol, shard_bounds
+    from oracle import oracle
+
+    hx = HostExchange()
+    rng = np.random.default_rng(77)  # same data on every rank
+    ok = True
+    for trial in range(20):
+        n = int(rng.integers(200, 30000))
+        levels = rng.choice([-0.3, 0.3], n // 50 + 1) if trial % 3 else rng.choice([-1.0, -0.2, 0.2, 1.0], n // 50 + 1)
+        x = (np.repeat(levels, 50)[:n] + 0.02 * rng.standard_normal(n)).astype(np.float32)
+        x[rng.random(n) < 0.1] = -4.0
+        if trial % 4 == 0:
+            s = int(rng.integers(0, n))
+            x[s: s + n // 3] = -4.0                      # a long gap: a shard may keep nothing at all
+        if trial == 7:
+            x[:] = -4.0                                   # nothing kept anywhere -> None
+        if trial == 9:
+            x[x > -4] = 0.25                              # constant signal: zero variance -> None
+        max_size = None if trial % 5 else 500
+        lo, hi = shard_bounds(n, world, align=int(rng.choice([1, 64])))[rank]
+        mine = x[lo:hi]
+        kept = mine[mine > -4]
+
+        def window_stats(a, b):
+            r = kept[a:b].astype(np.float64)
+            if len(r) == 0:
+                return [0.0, np.inf, -np.inf, 0.0, 0.0]
+            return [len(r), r.min(), r.max(), r.sum(), (r * r).sum()]
+
+        def histogram(a, b, edges):
+            exact = edges[0] + np.arange(len(edges)) * (edges[1] - edges[0])
+            return np.histogram(kept[a:b], bins=exact)[0]
+
+        def allgather(v):
+            return np.array(hx.allgather(np.asarray(v, dtype=np.int64)))
+
+        def allreduce(y):
+            t = torch.from_numpy(np.ascontiguousarray(y))
+            dist.all_reduce(t)
+            return t.numpy()
+
+        c = center_protocol(rank, world, len(kept), window_stats, histogram, allgather, allreduce, max_size)
+        ref = oracle.detect_center(x, max_size=max_size)
+        same = (c is None) == (ref is None) and (c is None or abs(c - ref) <= 2e-6 * max(1.0, abs(ref)))
+        ok = ok and same
+    res = hx.allgather(bool(ok))
+    if rank == 0:
+        open(os.path.join(tmp, "ok_center"), "w").write("1" if all(res) else "0")
+    dist.destroy_process_group()
+
+
+def test_distributed_center_protocol_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = 29450 + os.getpid() % 200
+    mp.spawn(_center_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "ok_center").read() == "1"

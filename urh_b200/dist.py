@@ -239,26 +239,23 @@ def demod_digitize_distributed(ctx, rank, world, sb: ShardBuffer, global_offset,
     return rows
 
 
-def detect_center_distributed(ctx, rank, world, sb: ShardBuffer, noise_mag, mod_type, d_qad, max_size=None):
-    """afp_demod of the shard into ``d_qad`` + the capture-wide detect_center, every rank ending with the same center.
-    Exchange (NCCL, a few hundred bytes + one histogram): kept-sample counts -> global rank window; per-rank window
-    partials {count, min, max, sum, sumsq} folded in rank order (deterministic) -> bin edges; histogram all-reduce."""
+def center_protocol(rank, world, kept, window_stats, histogram, allgather_i64, allreduce_sum_i64, max_size=None):
+    """The exchange behind a capture-wide detect_center, independent of where the numbers come from (GPU + NCCL in
+    ``detect_center_distributed``; numpy + gloo in tests/test_dist_cpu.py).
+      kept                      number of samples this shard keeps (qad > -4)
+      window_stats(lr0, lr1)    -> [count, min, max, sum, sumsq] of the kept samples of LOCAL rank [lr0, lr1)
+      histogram(lr0, lr1, edges)-> int64 counts of those samples for np.histogram(…, bins=edges)
+      allgather_i64(values)     -> array [world, len(values)]; allreduce_sum_i64(array) -> array
+    Every rank returns the same center (or None)."""
     from .ainterpretation.AutoInterpretation import center_rank_window, center_stats_from_window, pick_center_from_histogram, \
         center_bin_edges
-    from .device import DeviceArray
-    lib = ctx.lib
-    code = _lib.demod_mod_code(mod_type)
-    kept = C.c_int64(0)
-    ctx.check(lib.urh_afp_demod_tiles(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, float(noise_mag), code,
-                                      C.c_void_p(d_qad.ptr), int(rank > 0), C.byref(kept)))
-    counts = nccl_allgather_i64(ctx, world, [kept.value])[:, 0]
+    counts = np.asarray(allgather_i64([int(kept)]))[:, 0]
     total, offset = int(counts.sum()), int(counts[:rank].sum())
     r0, r1 = center_rank_window(total, max_size)
-    lr0 = min(max(r0 - offset, 0), kept.value)
-    lr1 = min(max(r1 - offset, 0), kept.value)
-    w = np.zeros(5, dtype=np.float64)
-    ctx.check(lib.urh_center_window_stats(ctx.handle, C.c_void_p(d_qad.ptr), sb.n, lr0, lr1, w.ctypes.data_as(C.c_void_p)))
-    parts = nccl_allgather_i64(ctx, world, w.view(np.int64)).view(np.float64)
+    lr0 = min(max(r0 - offset, 0), int(kept))
+    lr1 = min(max(r1 - offset, 0), int(kept))
+    w = np.ascontiguousarray(window_stats(lr0, lr1), dtype=np.float64)
+    parts = np.asarray(allgather_i64(w.view(np.int64))).view(np.float64)
     g = np.array([parts[:, 0].sum(), parts[:, 1].min(), parts[:, 2].max(), 0.0, 0.0])
     for q in range(world):  # rank order, so every rank (and every world size's replay) folds identically
         g[3] += parts[q, 3]
@@ -267,14 +264,41 @@ def detect_center_distributed(ctx, rank, world, sb: ShardBuffer, noise_mag, mod_
     edges = center_bin_edges(st)
     if edges is None:
         return None
-    nbins = len(edges) - 1
-    y = np.zeros(nbins, dtype=np.int64)
-    ctx.check(lib.urh_center_histogram_tiles(ctx.handle, C.c_void_p(d_qad.ptr), sb.n, lr0, lr1, C.c_double(edges[0]),
-                                             C.c_double(edges[1] - edges[0]), nbins, y.ctypes.data_as(C.c_void_p)))
-    d_hist = DeviceArray(ctx, (nbins,), np.int64)
-    d_hist.set(y)
-    ctx.check(lib.urh_nccl_allreduce_i64(ctx.handle, C.c_void_p(d_hist.ptr), nbins, 0))
-    return pick_center_from_histogram(d_hist.get(), edges)
+    y = allreduce_sum_i64(np.ascontiguousarray(histogram(lr0, lr1, edges), dtype=np.int64))
+    return pick_center_from_histogram(y, edges)
+
+
+def detect_center_distributed(ctx, rank, world, sb: ShardBuffer, noise_mag, mod_type, d_qad, max_size=None):
+    """afp_demod of the shard into ``d_qad`` + the capture-wide detect_center, every rank ending with the same center.
+    Exchange (NCCL, a few hundred bytes + one histogram): kept-sample counts -> global rank window; per-rank window
+    partials {count, min, max, sum, sumsq} folded in rank order (deterministic) -> bin edges; histogram all-reduce."""
+    from .device import DeviceArray
+    lib = ctx.lib
+    code = _lib.demod_mod_code(mod_type)
+    kept = C.c_int64(0)
+    ctx.check(lib.urh_afp_demod_tiles(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, float(noise_mag), code,
+                                      C.c_void_p(d_qad.ptr), int(rank > 0), C.byref(kept)))
+
+    def window_stats(lr0, lr1):
+        w = np.zeros(5, dtype=np.float64)
+        ctx.check(lib.urh_center_window_stats(ctx.handle, C.c_void_p(d_qad.ptr), sb.n, lr0, lr1, w.ctypes.data_as(C.c_void_p)))
+        return w
+
+    def histogram(lr0, lr1, edges):
+        nbins = len(edges) - 1
+        y = np.zeros(nbins, dtype=np.int64)
+        ctx.check(lib.urh_center_histogram_tiles(ctx.handle, C.c_void_p(d_qad.ptr), sb.n, lr0, lr1, C.c_double(edges[0]),
+                                                 C.c_double(edges[1] - edges[0]), nbins, y.ctypes.data_as(C.c_void_p)))
+        return y
+
+    def allreduce(y):
+        d_hist = DeviceArray(ctx, (len(y),), np.int64)
+        d_hist.set(y)
+        ctx.check(lib.urh_nccl_allreduce_i64(ctx.handle, C.c_void_p(d_hist.ptr), len(y), 0))
+        return d_hist.get()
+
+    return center_protocol(rank, world, kept.value, window_stats, histogram, lambda v: nccl_allgather_i64(ctx, world, v), allreduce,
+                           max_size)
 
 
 def demod_center_digitize_distributed(ctx, rank, world, sb: ShardBuffer, global_offset, n_total, noise_mag, mod_type, tolerance,
