@@ -159,17 +159,18 @@ __global__ void __launch_bounds__(128) k_cs_speculate(const void* __restrict__ i
 //   src[t][c*segs + j]   candidate whose samples are right in that segment, or 255 = "stepped here"
 //   segst[t][c*segs + j] the state at the start of a stepped segment (k_cs_fix recomputes those samples from it)
 // The chain itself is still serial, so it is run speculatively as well (pass 2a): the chunks are grouped into super-chunks
-// of CS_SUP chunks and one warp per (super-chunk, candidate k) runs the chain through the super-chunk ASSUMING it starts in
+// of T.sup chunks (>= 128 Ki samples) and one warp per (super-chunk, candidate k) runs the chain through the super-chunk ASSUMING it starts in
 // candidate k's start state.  Pass 2b (one warp) then only hops from super-chunk to super-chunk: the true state at a
 // super-chunk start almost always equals one of the assumptions (bitwise) -> take that chain's tables and end state; if
 // not, the warp runs the chain through that super-chunk itself (table family nbr).  Exactness is by construction as in
 // pass 1: a chain is only ever adopted when its starting state is bit-identical to the true one.
-#define CS_SUP 64
+#define CS_SUP_MIN 64              // chunks per super-chunk, at least; raised so that a super-chunk spans >= 128 Ki samples
 
 struct CsTables {
     uint8_t* src;     // [2 * nbr + 1][nseg]
     CsState* segst;   // [2 * nbr + 1][nseg]
     int64_t nseg;     // nchunks * segs
+    int sup;          // chunks per super-chunk
 };
 
 // one warp; returns the state after chunk hi-1.  acc[0..2] += {O(1) chunks, walked chunks, samples stepped}
@@ -312,8 +313,8 @@ __global__ void __launch_bounds__(128) k_cs_chains(const void* __restrict__ iq, 
     if (wid >= nsuper * nbr) return;
     const int64_t w = wid / nbr;
     const int k = (int)(wid % nbr);
-    int64_t lo = w * CS_SUP;
-    const int64_t hi = min(nchunks, lo + CS_SUP);
+    int64_t lo = w * T.sup;
+    const int64_t hi = min(nchunks, lo + T.sup);
     int64_t acc[3] = {0, 0, 0};
     CsState st;
     uint8_t* src = T.src + (int64_t)(family * nbr + k) * T.nseg;
@@ -349,11 +350,11 @@ __global__ void __launch_bounds__(128) k_cs_chains(const void* __restrict__ iq, 
 }
 
 // prev_live[w] = last super-chunk before w that holds at least one sample above the noise gate (-1: none)
-__global__ void k_cs_live(const int* __restrict__ chunk_cnt, int64_t nchunks, int64_t nsuper, int64_t* __restrict__ live) {
+__global__ void k_cs_live(const int* __restrict__ chunk_cnt, int64_t nchunks, int64_t nsuper, int sup, int64_t* __restrict__ live) {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nsuper) return;
     int64_t any = 0;
-    for (int64_t c = w * CS_SUP; c < min(nchunks, (w + 1) * CS_SUP); c++) any |= chunk_cnt[c] > 0 ? 1 : 0;
+    for (int64_t c = w * sup; c < min(nchunks, (w + 1) * (int64_t)sup); c++) any |= chunk_cnt[c] > 0 ? 1 : 0;
     live[w] = any;
 }
 __global__ void k_cs_prev_live(const int64_t* __restrict__ live, int64_t nsuper, int64_t* __restrict__ prev_live) {
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(32) k_cs_stitch(const void* __restrict__ iq, i
         w = 1;
     }
     for (; w < nsuper; w++) {
-        const int64_t lo = w * CS_SUP;
+        const int64_t lo = w * T.sup;
         const int64_t p = prev_live[w];
         // lanes 0..nbr-1: family A start states (candidate checkpoints); lanes 8..8+nbr-1: family B start states
         int m = -1;
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(32) k_cs_stitch(const void* __restrict__ iq, i
             if (lane == 0) chosen[w] = (uint8_t)(2 * nbr);
             redone++;
             st = cs_chain<DT>(iq, n, P, nchunks, nbr, ckpt, nonnoise, chunk_cnt, T.src + (int64_t)(2 * nbr) * T.nseg,
-                              T.segst + (int64_t)(2 * nbr) * T.nseg, first_shard, lo, min(nchunks, lo + CS_SUP), st, acc);
+                              T.segst + (int64_t)(2 * nbr) * T.nseg, first_shard, lo, min(nchunks, lo + T.sup), st, acc);
         }
     }
     if (lane == 0 && st_out) *st_out = st;
@@ -435,7 +436,7 @@ __global__ void k_cs_assemble(const float* __restrict__ cand, int64_t n, CsTable
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int64_t seg = i / CS_SEG;
-        const int64_t w = seg / ((int64_t)segs * CS_SUP);
+        const int64_t w = seg / ((int64_t)segs * T.sup);
         const uint8_t k = T.src[(int64_t)chosen[w] * T.nseg + seg];
         if (k != 255) out[i] = cand[(int64_t)k * n + i];
     }
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(128) k_cs_fix(const void* __restrict__ iq, int
     const int lane = threadIdx.x & 31;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < T.nseg; seg += nw) {
-        const int64_t w = seg / ((int64_t)P.segs * CS_SUP);
+        const int64_t w = seg / ((int64_t)P.segs * T.sup);
         const int64_t t = chosen[w];
         if (T.src[t * T.nseg + seg] != 255) continue;
         CsState st = T.segst[t * T.nseg + seg];
@@ -547,7 +548,8 @@ static int cs_speculate(urh_ctx* ctx, CsRun& R) {
     URH_CHECK(urh_arena(ctx, (size_t)R.nbr * R.nchunks * (R.P.segs + 1), &R.ckpt));
     URH_CHECK(urh_arena(ctx, (size_t)R.nchunks * R.P.segs, &R.nonnoise));
     R.T.nseg = R.nchunks * R.P.segs;
-    R.nsuper = urh_div_up(R.nchunks, CS_SUP);
+    R.T.sup = (int)max((int64_t)CS_SUP_MIN, urh_div_up((int64_t)131072, (int64_t)R.P.chunk));
+    R.nsuper = urh_div_up(R.nchunks, R.T.sup);
     URH_CHECK(urh_arena(ctx, (size_t)(2 * R.nbr + 1) * R.T.nseg, &R.T.src));
     URH_CHECK(urh_arena(ctx, (size_t)(2 * R.nbr + 1) * R.T.nseg, &R.T.segst));
     URH_CHECK(urh_arena(ctx, (size_t)2 * R.nsuper * R.nbr, &R.sup_end));
@@ -563,7 +565,7 @@ static int cs_speculate(urh_ctx* ctx, CsRun& R) {
     // pass 2a: the chains of every super-chunk under every assumption (independent of the true incoming state)
     const int64_t per = R.nsuper * R.nbr;
     URH_CUDA(ctx, cudaMemsetAsync(R.sup_acc, 0, (size_t)2 * per * 3 * sizeof(int64_t), ctx->stream));
-    URH_LAUNCH(ctx, k_cs_live, (unsigned)urh_div_up(R.nsuper, 128), 128, 0, R.chunk_cnt, R.nchunks, R.nsuper, R.live);
+    URH_LAUNCH(ctx, k_cs_live, (unsigned)urh_div_up(R.nsuper, 128), 128, 0, R.chunk_cnt, R.nchunks, R.nsuper, R.T.sup, R.live);
     URH_LAUNCH(ctx, k_cs_prev_live, 1, 32, 0, (const int64_t*)R.live, R.nsuper, R.prev_live);
     const unsigned gc = (unsigned)urh_div_up(per * 32, 128);
     CS_DISPATCH(R, k_cs_chains, gc, 128, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.T, R.first_shard, R.nsuper, 0,
