@@ -79,7 +79,7 @@ def main():
     emit("afp_demod ASK", timed(ctx, lambda: sf.afp_demod(d_iq, B.NOISE_MAG, "ASK", 2)), n, 12)
     emit("grab_pulse_lens (stand-alone, qad in HBM)", timed(ctx, lambda: sf.grab_pulse_lens(q, 0.0, 5, "FSK", 100)), n, 4, "incl. D2H of the pulse table")
     emit("detect_noise_level from IQ (no float64 magnitudes)", timed(ctx, lambda: AI.detect_noise_level_iq(d_iq)), n, 8)
-    emit("detect_center (count + 2 stat passes + histogram)", timed(ctx, lambda: AI.detect_center(q)), n, 4, "reads qad 4x in this round")
+    emit("detect_center stand-alone (tile statistics pass + histogram pass over qad)", timed(ctx, lambda: AI.detect_center(q)), n, 8, "incl. host peak picking")
     mags = util.get_magnitudes(d_iq)
     emit("get_magnitudes (float64 out)", timed(ctx, lambda: util.get_magnitudes(d_iq)), n, 16)
     emit("segment_messages_from_magnitudes (float64 in)", timed(ctx, lambda: cai.segment_messages_from_magnitudes(mags, B.NOISE_MAG)), n, 8)
