@@ -307,12 +307,20 @@ struct HistBins {
     }
 };
 
-// A demodulated capture piles its samples onto a handful of bins.  Each thread keeps four (bin, count) pairs in registers;
-// a sample whose bin is not among them takes over the least used pair (whose count goes to the histogram).
+// A demodulated capture piles its samples onto a handful of bins.  Each thread keeps four bins in registers as float
+// INTERVALS [lo, hi) with a count: a sample is compared with the four intervals directly (no bin index is computed on a
+// hit); only a sample that falls into none of them is binned through the table and takes over the least used entry, whose
+// count goes to the histogram.
 struct HistCache {
+    float lo0, hi0, lo1, hi1, lo2, hi2, lo3, hi3;
     int h0, h1, h2, h3;
     unsigned c0, c1, c2, c3;
-    __device__ __forceinline__ void init() { h0 = h1 = h2 = h3 = -2; c0 = c1 = c2 = c3 = 0u; }
+    __device__ __forceinline__ void init() {
+        lo0 = lo1 = lo2 = lo3 = INFINITY;   // empty interval: nothing is >= +inf
+        hi0 = hi1 = hi2 = hi3 = -INFINITY;
+        h0 = h1 = h2 = h3 = 0;
+        c0 = c1 = c2 = c3 = 0u;
+    }
 };
 
 template <bool SMEM>
@@ -321,34 +329,44 @@ __device__ __forceinline__ void hist_bump(unsigned int* s_hist, unsigned long lo
     else atomicAdd(&hist[k], (unsigned long long)c);
 }
 
-template <bool SMEM>
-__device__ __forceinline__ void hist_miss(HistCache& hc, unsigned int* s_hist, unsigned long long* hist, int k) {
+// f lies inside the histogram range but in none of the cached bins
+template <bool SMEM, bool FAST>
+__device__ __forceinline__ void hist_miss(HistCache& hc, const HistBins& hb, unsigned int* s_hist, unsigned long long* hist, float f) {
+    const int k = hb.bin_of<FAST>(f);
+    if (k < 0) return;
+    // the cached interval must reproduce the validity test as well: nothing below f_min, the last bin closed at f_hi
+    const float lo = fmaxf(hb.fe[k], hb.f_min);
+    const float hi = (k == hb.nbins - 1) ? nextafterf(hb.f_hi, INFINITY) : hb.fe[k + 1];
     unsigned cm = hc.c0; int which = 0;
     if (hc.c1 < cm) { cm = hc.c1; which = 1; }
     if (hc.c2 < cm) { cm = hc.c2; which = 2; }
     if (hc.c3 < cm) { cm = hc.c3; which = 3; }
     const int old = which == 0 ? hc.h0 : which == 1 ? hc.h1 : which == 2 ? hc.h2 : hc.h3;
     if (cm) hist_bump<SMEM>(s_hist, hist, old, cm);
-    if (which == 0) { hc.h0 = k; hc.c0 = 1u; }
-    else if (which == 1) { hc.h1 = k; hc.c1 = 1u; }
-    else if (which == 2) { hc.h2 = k; hc.c2 = 1u; }
-    else { hc.h3 = k; hc.c3 = 1u; }
+    if (which == 0) { hc.h0 = k; hc.c0 = 1u; hc.lo0 = lo; hc.hi0 = hi; }
+    else if (which == 1) { hc.h1 = k; hc.c1 = 1u; hc.lo1 = lo; hc.hi1 = hi; }
+    else if (which == 2) { hc.h2 = k; hc.c2 = 1u; hc.lo2 = lo; hc.hi2 = hi; }
+    else { hc.h3 = k; hc.c3 = 1u; hc.lo3 = lo; hc.hi3 = hi; }
 }
 
-template <bool SMEM>
-__device__ __forceinline__ void hist_put(HistCache& hc, unsigned int* s_hist, unsigned long long* hist, int k) {
-    // four compare + predicated-increment pairs (spelled out: the compiler otherwise materialises count+1 and selects)
+template <bool SMEM, bool FAST>
+__device__ __forceinline__ void hist_put(HistCache& hc, const HistBins& hb, unsigned int* s_hist, unsigned long long* hist, float f) {
+    // per entry: two compares chained into one predicate and a predicated increment (spelled out in PTX: the compiler
+    // otherwise turns each increment into select + add + move); miss = inside the histogram's range but in no cached bin
     unsigned miss;
-    asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
-        "setp.eq.s32 p0, %5, %6;\n\t@p0 add.u32 %0, %0, 1;\n\t"
-        "setp.eq.s32 p1, %5, %7;\n\t@p1 add.u32 %1, %1, 1;\n\t"
-        "setp.eq.s32 p2, %5, %8;\n\t@p2 add.u32 %2, %2, 1;\n\t"
-        "setp.eq.s32 p3, %5, %9;\n\t@p3 add.u32 %3, %3, 1;\n\t"
+    asm("{\n\t.reg .pred p0, p1, p2, p3, pv;\n\t"
+        "setp.ge.f32 p0, %5, %6;\n\tsetp.lt.and.f32 p0, %5, %7, p0;\n\t@p0 add.u32 %0, %0, 1;\n\t"
+        "setp.ge.f32 p1, %5, %8;\n\tsetp.lt.and.f32 p1, %5, %9, p1;\n\t@p1 add.u32 %1, %1, 1;\n\t"
+        "setp.ge.f32 p2, %5, %10;\n\tsetp.lt.and.f32 p2, %5, %11, p2;\n\t@p2 add.u32 %2, %2, 1;\n\t"
+        "setp.ge.f32 p3, %5, %12;\n\tsetp.lt.and.f32 p3, %5, %13, p3;\n\t@p3 add.u32 %3, %3, 1;\n\t"
         "or.pred p0, p0, p1;\n\tor.pred p2, p2, p3;\n\tor.pred p0, p0, p2;\n\t"
-        "selp.u32 %4, 0, 1, p0;\n\t}"
+        "setp.ge.f32 pv, %5, %14;\n\tsetp.le.and.f32 pv, %5, %15, pv;\n\t"
+        "and.pred pv, pv, !p0;\n\t"
+        "selp.u32 %4, 1, 0, pv;\n\t}"
         : "+r"(hc.c0), "+r"(hc.c1), "+r"(hc.c2), "+r"(hc.c3), "=r"(miss)
-        : "r"(k), "r"(hc.h0), "r"(hc.h1), "r"(hc.h2), "r"(hc.h3));
-    if (miss && k >= 0) hist_miss<SMEM>(hc, s_hist, hist, k);
+        : "f"(f), "f"(hc.lo0), "f"(hc.hi0), "f"(hc.lo1), "f"(hc.hi1), "f"(hc.lo2), "f"(hc.hi2), "f"(hc.lo3), "f"(hc.hi3),
+          "f"(hb.f_min), "f"(hb.f_hi));
+    if (miss) hist_miss<SMEM, FAST>(hc, hb, s_hist, hist, f);
 }
 
 template <bool SMEM>
@@ -399,16 +417,16 @@ __global__ void __launch_bounds__(256, 4) k_hist_interior(const float* __restric
                     }
 #pragma unroll
                     for (int j = 0; j < RB; j++) {
-                        hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(cur[j].x));
-                        hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(cur[j].y));
-                        hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(cur[j].z));
-                        hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(cur[j].w));
+                        hist_put<SMEM, FAST>(hc, hb, s_hist, hist, cur[j].x);
+                        hist_put<SMEM, FAST>(hc, hb, s_hist, hist, cur[j].y);
+                        hist_put<SMEM, FAST>(hc, hb, s_hist, hist, cur[j].z);
+                        hist_put<SMEM, FAST>(hc, hb, s_hist, hist, cur[j].w);
                     }
 #pragma unroll
                     for (int j = 0; j < RB; j++) cur[j] = nxt[j];
                 }
             } else {
-                for (int j = lane; j < URH_TILE; j += 32) hist_put<SMEM>(hc, s_hist, hist, hb.bin_of<FAST>(x[base + j]));
+                for (int j = lane; j < URH_TILE; j += 32) hist_put<SMEM, FAST>(hc, hb, s_hist, hist, x[base + j]);
             }
         }
     }
