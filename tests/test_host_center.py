@@ -61,3 +61,41 @@ def test_rank_window_and_stats():
     assert AI.center_bin_edges(empty) is None
     const = AI.center_stats_from_window(100, 5, 95, np.array([90.0, 1.0, 1.0, 90.0, 90.0]))
     assert AI.center_bin_edges(const) is None  # zero variance: arange raises -> no center
+
+
+def test_fsk_peak_test_from_spectrum_features_equals_reference_rule():
+    """detect_modulation's FSK rule (AutoInterpretation.py:196-206) evaluated from the three spectrum features the device
+    returns (arg-max, best bin >= 10 away, the 19 bins around the arg-max) == the rule on the full spectrum."""
+    rng = np.random.default_rng(3)
+    for trial in range(2000):
+        P = int(rng.choice([32, 64, 256, 1024]))
+        kind = trial % 5
+        fft = rng.uniform(0, 50, P)
+        if kind == 1:
+            fft[rng.integers(0, P)] += 500                      # one peak
+        elif kind == 2:
+            a = int(rng.integers(0, P))
+            fft[a] += 500
+            fft[(a + int(rng.integers(10, P - 10))) % P] += float(rng.choice([80, 150, 400]))   # a second peak far away
+        elif kind == 3:
+            a = int(rng.integers(0, P))
+            fft[max(0, a - 9):a + 10] += rng.uniform(200, 900, len(fft[max(0, a - 9):a + 10]))  # a broad peak: 19 big bins
+            fft[(a + P // 2) % P] += float(rng.choice([0, 120, 300, 950]))
+        elif kind == 4:
+            fft = rng.uniform(90, 110, P)                       # everything around the threshold
+        fft = fft.astype(np.float32)
+        ten = np.argsort(fft)[::-1][0:10]
+        ref = bool(any(abs(i - ten[0]) >= 10 and fft[i] >= 100 for i in ten))
+        g = int(np.argmax(fft))
+        assert g == ten[0]
+        spec = np.full(23, -1.0)
+        spec[0], spec[1] = g, fft[g]
+        far = [i for i in range(P) if abs(i - g) >= 10]
+        if far:
+            f = max(far, key=lambda i: fft[i])
+            spec[2], spec[3] = f, fft[f]
+        for j in range(19):
+            i = g - 9 + j
+            if 0 <= i < P:
+                spec[4 + j] = fft[i]
+        assert AI._fsk_peak_test(spec) == ref, (trial, P)
