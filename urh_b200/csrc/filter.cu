@@ -140,9 +140,71 @@ __global__ void k_conv_c128(const float2* __restrict__ x, int64_t n, const doubl
     }
 }
 
+// The same convolution, tiled: the block converts its input span to double ONCE into shared memory (the naive kernel
+// converts every sample once per tap -- the float->double converter, not the FMA pipe, was its limit), the taps sit in
+// shared memory too, and every thread produces CONV_PER consecutive outputs from a sliding register window: one 16-byte
+// shared-memory read feeds 4 * CONV_PER double FMAs.  CONV_PER is odd so that the lanes' 16-byte reads (stride CONV_PER * 16 B)
+// fall into distinct banks.  Same accumulation order per output as k_conv_c128 (ascending tap index, fused multiply-adds).
+#define CONV_PER 5
+#define CONV_THREADS 256
+#define CONV_TILE (CONV_PER * CONV_THREADS)
+#define CONV_MAX_TAPS 768
+__global__ void __launch_bounds__(CONV_THREADS) k_conv_c128_tiled(const float2* __restrict__ x, int64_t n, const double2* __restrict__ h, int m,
+                                                                 int64_t offset, int64_t out_len, float2* __restrict__ y) {
+    extern __shared__ double2 s_conv[];
+    double2* s_h = s_conv;            // [m]
+    double2* s_x = s_conv + m;        // [CONV_TILE + m - 1]: s_x[i] = x[first + i], zero outside the array
+    for (int j = threadIdx.x; j < m; j += CONV_THREADS) s_h[j] = h[j];
+    const int span = CONV_TILE + m - 1;
+    for (int64_t k0 = (int64_t)blockIdx.x * CONV_TILE; k0 < out_len; k0 += (int64_t)gridDim.x * CONV_TILE) {
+        const int64_t first = k0 + offset - (m - 1);   // input index of s_x[0]
+        __syncthreads();                                // the previous tile's readers are done
+        for (int i = threadIdx.x; i < span; i += CONV_THREADS) {
+            const int64_t g = first + i;
+            double2 v = make_double2(0.0, 0.0);
+            if (g >= 0 && g < n) { const float2 f = x[g]; v = make_double2((double)f.x, (double)f.y); }
+            s_x[i] = v;
+        }
+        __syncthreads();
+        // output o (tile-relative) at tap j reads input index (k0 + o + offset) - j = first + (o + m - 1 - j)
+        const int o0 = threadIdx.x * CONV_PER;
+        double2 w[CONV_PER];   // w[i] = s_x[o0 + i + m - 1 - j]
+#pragma unroll
+        for (int i = 0; i < CONV_PER; i++) w[i] = s_x[o0 + i + m - 1];
+        double re[CONV_PER], im[CONV_PER];
+#pragma unroll
+        for (int i = 0; i < CONV_PER; i++) { re[i] = 0.0; im[i] = 0.0; }
+        for (int j = 0; j < m; j++) {
+            const double2 c = s_h[j];
+#pragma unroll
+            for (int i = 0; i < CONV_PER; i++) {
+                re[i] = fma(w[i].x, c.x, re[i]);
+                re[i] = fma(-w[i].y, c.y, re[i]);
+                im[i] = fma(w[i].x, c.y, im[i]);
+                im[i] = fma(w[i].y, c.x, im[i]);
+            }
+            // slide the window one input sample down
+#pragma unroll
+            for (int i = CONV_PER - 1; i > 0; i--) w[i] = w[i - 1];
+            if (j + 1 < m) w[0] = s_x[o0 + m - 2 - j];
+        }
+#pragma unroll
+        for (int i = 0; i < CONV_PER; i++) {
+            const int64_t k = k0 + o0 + i;
+            if (k < out_len) y[k] = make_float2((float)re[i], (float)im[i]);
+        }
+    }
+}
+
 extern "C" int urh_convolve_c128(urh_ctx* ctx, const float* d_x, int64_t n, const double* d_taps, int m, int64_t offset,
                                  int64_t out_len, float* d_y) {
     if (out_len <= 0) return URH_OK;
+    if (m >= 1 && m <= CONV_MAX_TAPS) {
+        const size_t smem = (size_t)(m + CONV_TILE + m - 1) * sizeof(double2);   // <= 44.5 KB for m <= 768
+        const unsigned grid = (unsigned)min(urh_div_up(out_len, CONV_TILE), (int64_t)ctx->sm_count * 8);
+        URH_LAUNCH(ctx, k_conv_c128_tiled, grid, CONV_THREADS, smem, (const float2*)d_x, n, (const double2*)d_taps, m, offset, out_len, (float2*)d_y);
+        return URH_OK;
+    }
     const unsigned grid = (unsigned)min(urh_div_up(out_len, 256), (int64_t)ctx->sm_count * 32);
     URH_LAUNCH(ctx, k_conv_c128, grid, 256, 0, (const float2*)d_x, n, (const double2*)d_taps, m, offset, out_len, (float2*)d_y);
     return URH_OK;
