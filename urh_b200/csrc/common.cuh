@@ -69,6 +69,7 @@ struct urh_ctx {
     void* center_prefix;  // tile rank prefix left by urh_afp_demod_stats for urh_center_histogram_tiles (arena)
     void* nccl_comm;
     void* nccl_stage;
+    void* nccl_hstage;  // pinned twin of nccl_stage
     int nccl_rank, nccl_world;
 };
 

@@ -38,6 +38,7 @@ extern "C" int urh_ctx_create(int device, urh_ctx** out) {
     ctx->center_n = 0;
     ctx->nccl_comm = nullptr;
     ctx->nccl_stage = nullptr;
+    ctx->nccl_hstage = nullptr;
     ctx->nccl_rank = 0;
     ctx->nccl_world = 1;
     if (cudaSetDevice(device) != cudaSuccess) {

@@ -155,16 +155,56 @@ extern "C" int urh_nccl_gatherv(urh_ctx* ctx, const void* d_send, void* d_recv, 
 
 // all-gather of a few host bytes per rank through a device staging buffer (metadata of the sharded digitizer:
 // cheaper than a TCP round trip through the launcher's process group)
+static int need_stage(urh_ctx* ctx) {
+    if (!ctx->nccl_stage) URH_CUDA(ctx, cudaMalloc(&ctx->nccl_stage, 65536));
+    if (!ctx->nccl_hstage) URH_CUDA(ctx, cudaHostAlloc(&ctx->nccl_hstage, 65536, cudaHostAllocDefault));
+    return URH_OK;
+}
+
 extern "C" int urh_nccl_allgather_host(urh_ctx* ctx, const void* h_send, void* h_recv, size_t bytes_per_rank) {
     URH_CHECK(need_comm(ctx));
-    if (!ctx->nccl_stage) URH_CUDA(ctx, cudaMalloc(&ctx->nccl_stage, 65536));
+    URH_CHECK(need_stage(ctx));
     const size_t total = bytes_per_rank * (size_t)ctx->nccl_world;
-    if (bytes_per_rank + total > 65536) URH_FAIL(ctx, URH_ERR_INVALID, "allgather_host: payload too large");
+    const size_t send_pad = (bytes_per_rank + 255) & ~(size_t)255;
+    if (send_pad + total > 65536) URH_FAIL(ctx, URH_ERR_INVALID, "allgather_host: payload too large");
+    // pinned staging on the host side: the copies are truly asynchronous and the caller's (pageable) buffers are touched
+    // by plain memcpy only
     char* d_send = (char*)ctx->nccl_stage;
-    char* d_recv = d_send + ((bytes_per_rank + 255) & ~(size_t)255);
-    URH_CUDA(ctx, cudaMemcpyAsync(d_send, h_send, bytes_per_rank, cudaMemcpyHostToDevice, ctx->stream));
+    char* d_recv = d_send + send_pad;
+    char* p_send = (char*)ctx->nccl_hstage;
+    char* p_recv = p_send + send_pad;
+    memcpy(p_send, h_send, bytes_per_rank);
+    URH_CUDA(ctx, cudaMemcpyAsync(d_send, p_send, bytes_per_rank, cudaMemcpyHostToDevice, ctx->stream));
     URH_NCCL(ctx, g_nccl.AllGather(d_send, d_recv, bytes_per_rank, URH_NCCL_UINT8, (urh_ncclComm_t)ctx->nccl_comm, ctx->stream));
-    URH_CUDA(ctx, cudaMemcpyAsync(h_recv, d_recv, total, cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaMemcpyAsync(p_recv, d_recv, total, cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(h_recv, p_recv, total);
+    return URH_OK;
+}
+
+// in-place all-reduce (op: 0 sum, 1 max, 2 min) of a small host int64 array through the same staging buffers
+// (the histogram of the capture-wide detect_center: a few thousand bins)
+extern "C" int urh_nccl_allreduce_host_i64(urh_ctx* ctx, int64_t* h_buf, int64_t count, int op) {
+    URH_CHECK(need_comm(ctx));
+    URH_CHECK(need_stage(ctx));
+    if (count <= 0) return URH_OK;
+    const int o = op == 0 ? URH_NCCL_SUM : (op == 1 ? URH_NCCL_MAX : URH_NCCL_MIN);
+    const size_t bytes = (size_t)count * sizeof(int64_t);
+    if (bytes <= 65536) {
+        memcpy(ctx->nccl_hstage, h_buf, bytes);
+        URH_CUDA(ctx, cudaMemcpyAsync(ctx->nccl_stage, ctx->nccl_hstage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        URH_NCCL(ctx, g_nccl.AllReduce(ctx->nccl_stage, ctx->nccl_stage, (size_t)count, URH_NCCL_INT64, o, (urh_ncclComm_t)ctx->nccl_comm, ctx->stream));
+        URH_CUDA(ctx, cudaMemcpyAsync(ctx->nccl_hstage, ctx->nccl_stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(h_buf, ctx->nccl_hstage, bytes);
+        return URH_OK;
+    }
+    int64_t* d = nullptr;
+    URH_CUDA(ctx, cudaMallocAsync((void**)&d, bytes, ctx->stream));
+    URH_CUDA(ctx, cudaMemcpyAsync(d, h_buf, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    URH_NCCL(ctx, g_nccl.AllReduce(d, d, (size_t)count, URH_NCCL_INT64, o, (urh_ncclComm_t)ctx->nccl_comm, ctx->stream));
+    URH_CUDA(ctx, cudaMemcpyAsync(h_buf, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaFreeAsync(d, ctx->stream));
     URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return URH_OK;
 }

@@ -292,10 +292,9 @@ def detect_center_distributed(ctx, rank, world, sb: ShardBuffer, noise_mag, mod_
         return y
 
     def allreduce(y):
-        d_hist = DeviceArray(ctx, (len(y),), np.int64)
-        d_hist.set(y)
-        ctx.check(lib.urh_nccl_allreduce_i64(ctx.handle, C.c_void_p(d_hist.ptr), len(y), 0))
-        return d_hist.get()
+        y = np.ascontiguousarray(y, dtype=np.int64)
+        ctx.check(lib.urh_nccl_allreduce_host_i64(ctx.handle, y.ctypes.data_as(C.c_void_p), len(y), 0))
+        return y
 
     return center_protocol(rank, world, kept.value, window_stats, histogram, lambda v: nccl_allgather_i64(ctx, world, v), allreduce,
                            max_size)
