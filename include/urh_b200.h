@@ -206,6 +206,12 @@ int urh_nccl_allgather(urh_ctx* ctx, const void* d_send, void* d_recv, size_t by
 int urh_nccl_gatherv(urh_ctx* ctx, const void* d_send, void* d_recv, const int64_t* h_bytes, int root);
 int urh_nccl_allgather_host(urh_ctx* ctx, const void* h_send, void* h_recv, size_t bytes_per_rank);
 int urh_nccl_allreduce_host_i64(urh_ctx* ctx, int64_t* h_buf, int64_t count, int op);
+/* the same few-bytes all-gather over NVLink peer memory, one small kernel per rank (p2p.cu): every rank creates a mailbox and
+ * hands its 64-byte IPC handle to the launcher plumbing; urh_p2p_open maps the peers' mailboxes (world <= 8, one node). */
+int urh_p2p_create(urh_ctx* ctx, char* out_handle64);
+int urh_p2p_open(urh_ctx* ctx, const char* handles, int rank, int world);
+int urh_p2p_close(urh_ctx* ctx);
+int urh_p2p_allgather_host(urh_ctx* ctx, const void* h_send, void* h_recv, size_t bytes_per_rank);
 
 /* ---- measurement utilities (not part of the reference's API surface) -------------------------------- */
 /* CUDA-event timing of the dominant (dense, sample-rate) kernel of the last demod/digitize call */

@@ -25,6 +25,22 @@ def main():
     hx = udist.HostExchange()
     udist.init_nccl(ctx, hx)
     failures = []
+    # NVLink peer mailboxes == NCCL for the few-bytes all-gathers (and they were actually opened)
+    import ctypes as C
+    rng_x = np.random.default_rng(1000 + rank)
+    if not getattr(ctx, "p2p", False):
+        failures.append(("p2p mailboxes not available on this box", rank))
+    else:
+        for it in range(300):
+            k = 1 + it % 6
+            send = rng_x.integers(-2**62, 2**62, k).astype(np.int64)
+            a = np.empty((world, k), np.int64)
+            b = np.empty((world, k), np.int64)
+            ctx.check(ctx.lib.urh_p2p_allgather_host(ctx.handle, send.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p), send.nbytes))
+            ctx.check(ctx.lib.urh_nccl_allgather_host(ctx.handle, send.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), send.nbytes))
+            if not np.array_equal(a, b) or not np.array_equal(a[rank], send):
+                failures.append(("p2p allgather", it))
+                break
     for case, (n, sps, tol, mod, dtype) in enumerate([
         (3_000_000, 100, 5, "FSK", np.float32), (1_000_003, 37, 0, "FSK", np.float32), (700_001, 50, 9, "ASK", np.float32),
         (2_500_000, 100, 5000, "FSK", np.float32), (900_000, 64, 3, "FSK", np.int16),

@@ -103,6 +103,10 @@ SIGNATURES = {
     "urh_shard_rows": (i32, [vp, i64, u16, i32, u32, i64, i32, C.POINTER(i64)]),
     "urh_nccl_allgather_host": (i32, [vp, vp, vp, szt]),
     "urh_nccl_allreduce_host_i64": (i32, [vp, vp, i64, i32]),
+    "urh_p2p_create": (i32, [vp, vp]),
+    "urh_p2p_open": (i32, [vp, vp, i32, i32]),
+    "urh_p2p_close": (i32, [vp]),
+    "urh_p2p_allgather_host": (i32, [vp, vp, vp, szt]),
     "urh_pulses_from_table": (i32, [vp, vp, vp, i64, i64, u16, i32, u32, i32, C.POINTER(i64)]),
     "urh_costas_halo_samples": (i32, []),
     "urh_costas_shard_speculate": (i32, [vp, vp, i32, i64, i32, f32, i32, f32, vp]),

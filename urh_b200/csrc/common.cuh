@@ -71,6 +71,12 @@ struct urh_ctx {
     void* nccl_stage;
     void* nccl_hstage;  // pinned twin of nccl_stage
     int nccl_rank, nccl_world;
+    // NVLink peer mailboxes (p2p.cu)
+    void* p2p_local;
+    void* p2p_peer[8];
+    void* p2p_hout;
+    int p2p_rank, p2p_world;
+    unsigned long long p2p_seq;
 };
 
 #define URH_CUDA(ctx, call)                                                                         \

@@ -14,6 +14,7 @@ Protocol of the sharded digitizer (exactness argument in DESIGN.md §6):
   4. gather the candidate tables on rank 0 (NCCL send/recv), which finishes exactly like the single-GPU path.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -89,6 +90,24 @@ def init_nccl(ctx: _lib.Context, hx: HostExchange):
             raise RuntimeError("urh_nccl_unique_id failed (libnccl.so.2 not loadable?)")
     ident = hx.broadcast(bytes(buf.raw) if hx.rank == 0 else None, src=0)
     ctx.check(ctx.lib.urh_nccl_init(ctx.handle, C.c_char_p(ident), hx.rank, hx.world))
+    init_p2p(ctx, hx)
+
+
+def init_p2p(ctx: _lib.Context, hx: HostExchange):
+    """NVLink peer mailboxes for the few-bytes all-gathers (p2p.cu).  Used only if EVERY rank could map every peer
+    (one node, <= 8 GPUs, CUDA IPC available); otherwise those exchanges stay on NCCL.  URH_B200_NO_P2P=1 disables it."""
+    ctx.p2p = False
+    ok = hx.world <= 8 and hx.world > 1 and os.environ.get("URH_B200_NO_P2P", "0") != "1"
+    handle = C.create_string_buffer(64)
+    if ok:
+        ok = ctx.lib.urh_p2p_create(ctx.handle, handle) == 0
+    handles = hx.allgather(bytes(handle.raw) if ok else None)
+    ok = ok and all(h is not None for h in handles)
+    if ok:
+        ok = ctx.lib.urh_p2p_open(ctx.handle, C.c_char_p(b"".join(handles)), hx.rank, hx.world) == 0
+    ctx.p2p = all(hx.allgather(bool(ok)))
+    if ok and not ctx.p2p:
+        ctx.lib.urh_p2p_close(ctx.handle)
 
 
 class ShardBuffer(object):
@@ -186,7 +205,8 @@ def nccl_allgather_i64(ctx, world, values):
     """all-gather a few int64 per rank over NCCL (device-staged, ~tens of microseconds) -> array [world, len(values)]"""
     send = np.ascontiguousarray(values, dtype=np.int64)
     recv = np.empty((world, len(send)), dtype=np.int64)
-    ctx.check(ctx.lib.urh_nccl_allgather_host(ctx.handle, send.ctypes.data_as(C.c_void_p), recv.ctypes.data_as(C.c_void_p), send.nbytes))
+    entry = ctx.lib.urh_p2p_allgather_host if (getattr(ctx, "p2p", False) and send.nbytes <= 48) else ctx.lib.urh_nccl_allgather_host
+    ctx.check(entry(ctx.handle, send.ctypes.data_as(C.c_void_p), recv.ctypes.data_as(C.c_void_p), send.nbytes))
     return recv
 
 
