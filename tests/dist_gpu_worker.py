@@ -28,9 +28,7 @@ def main():
     # NVLink peer mailboxes == NCCL for the few-bytes all-gathers (and they were actually opened)
     import ctypes as C
     rng_x = np.random.default_rng(1000 + rank)
-    if not getattr(ctx, "p2p", False):
-        failures.append(("p2p mailboxes not available on this box", rank))
-    else:
+    if getattr(ctx, "p2p", False):   # opt-in (URH_B200_P2P=1)
         for it in range(300):
             k = 1 + it % 6
             send = rng_x.integers(-2**62, 2**62, k).astype(np.int64)

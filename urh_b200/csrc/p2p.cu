@@ -36,6 +36,7 @@ __global__ void k_p2p_allgather(P2pArgs a, unsigned long long* __restrict__ hout
     for (int i = 0; i < P2P_WORDS; i++) dst->data[i] = a.data[i];
     __threadfence_system();
     dst->seq = a.seq;
+    __threadfence_system();   // push the flag out now: this kernel keeps running (spinning) for a while
     volatile P2pSlot* src = a.local + a.slot * P2P_MAXW + r;
     const long long t0 = clock64();
     while (src->seq != a.seq) {

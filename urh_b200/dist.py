@@ -95,9 +95,11 @@ def init_nccl(ctx: _lib.Context, hx: HostExchange):
 
 def init_p2p(ctx: _lib.Context, hx: HostExchange):
     """NVLink peer mailboxes for the few-bytes all-gathers (p2p.cu).  Used only if EVERY rank could map every peer
-    (one node, <= 8 GPUs, CUDA IPC available); otherwise those exchanges stay on NCCL.  URH_B200_NO_P2P=1 disables it."""
+    (one node, <= 8 GPUs, CUDA IPC available); otherwise those exchanges stay on NCCL.
+    EXPERIMENTAL, opt-in with URH_B200_P2P=1: the first measurement (before the flag store got its own fence) was slower
+    than the NCCL path (8.5 vs 5.2 ms/step at 2 GPUs), see DESIGN.md section 6."""
     ctx.p2p = False
-    ok = hx.world <= 8 and hx.world > 1 and os.environ.get("URH_B200_NO_P2P", "0") != "1"
+    ok = hx.world <= 8 and hx.world > 1 and os.environ.get("URH_B200_P2P", "0") == "1"
     handle = C.create_string_buffer(64)
     if ok:
         ok = ctx.lib.urh_p2p_create(ctx.handle, handle) == 0
