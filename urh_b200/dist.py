@@ -96,8 +96,9 @@ def init_nccl(ctx: _lib.Context, hx: HostExchange):
 def init_p2p(ctx: _lib.Context, hx: HostExchange):
     """NVLink peer mailboxes for the few-bytes all-gathers (p2p.cu).  Used only if EVERY rank could map every peer
     (one node, <= 8 GPUs, CUDA IPC available); otherwise those exchanges stay on NCCL.
-    EXPERIMENTAL, opt-in with URH_B200_P2P=1: the first measurement (before the flag store got its own fence) was slower
-    than the NCCL path (8.5 vs 5.2 ms/step at 2 GPUs), see DESIGN.md section 6."""
+    Opt-in with URH_B200_P2P=1: measured on par with the NCCL path at 2 GPUs (5.23 vs 5.22 ms/step with center detection,
+    3.43 vs 3.46 fused) -- the per-step overhead of a sharded capture is rank skew and the small device stages between
+    the exchanges, not the collective's latency -- so NCCL stays the default."""
     ctx.p2p = False
     ok = hx.world <= 8 and hx.world > 1 and os.environ.get("URH_B200_P2P", "0") == "1"
     handle = C.create_string_buffer(64)
