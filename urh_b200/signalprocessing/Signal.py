@@ -37,6 +37,35 @@ class _Event(object):
             s(*args)
 
 
+class _Tracked(object):
+    """One demodulation parameter of a Signal.  Assigning a DIFFERENT value stores it and then, as configured: drops the
+    cached demodulation, fires ``<name>_changed`` with the new value, asks for a protocol update (unless updates are
+    blocked).  Assigning the current value does nothing.  This is the reference's setter pattern (Signal.py:215-400),
+    stated once instead of per property."""
+
+    def __init__(self, cast=None, drops_qad=False, event=True, update=True):
+        self.cast, self.drops_qad, self.event, self.update = cast, drops_qad, event, update
+
+    def __set_name__(self, owner, name):
+        self.name, self.slot = name, "_p_" + name
+
+    def __get__(self, obj, owner=None):
+        return self if obj is None else getattr(obj, self.slot)
+
+    def __set__(self, obj, value):
+        if self.cast is not None:
+            value = self.cast(value)
+        if getattr(obj, self.slot) == value:
+            return
+        setattr(obj, self.slot, value)
+        if self.drops_qad:
+            obj._drop_qad()
+        if self.event:
+            getattr(obj, self.name + "_changed").emit(value)
+        if self.update:
+            obj._needs_update()
+
+
 class Signal(object):
     MODULATION_TYPES = ["ASK", "FSK", "PSK", "QAM"]
     _EVENTS = ("samples_per_symbol_changed", "tolerance_changed", "noise_threshold_changed", "center_changed",
@@ -46,18 +75,16 @@ class Signal(object):
     def __init__(self, filename: str, name="Signal", modulation: str = None, sample_rate: float = 1e6, timestamp: float = 0, parent=None):
         for e in self._EVENTS:
             setattr(self, e, _Event())
-        self.__name = name
-        self.__tolerance = 5
-        self.__samples_per_symbol = 100
-        self.__pause_threshold = 8
-        self.__message_length_divisor = 1
-        self.__costas_loop_bandwidth = 0.1
+        # parameter slots are filled directly: construction fires no events
+        defaults = dict(name=name, tolerance=5, samples_per_symbol=100, pause_threshold=8, message_length_divisor=1,
+                        costas_loop_bandwidth=0.1, center=0, sample_rate=sample_rate, bits_per_symbol=1, center_spacing=1,
+                        modulation_type="FSK" if modulation is None else modulation)
+        for key, value in defaults.items():
+            setattr(self, "_p_" + key, value)
         self._qad = None
         self._qad_dev = None
-        self.__center = 0
         self._noise_threshold = 0
-        self.__sample_rate = sample_rate
-        self.__timestamp = timestamp
+        self.timestamp = timestamp
         self.noise_min_plot = 0
         self.noise_max_plot = 0
         self.block_protocol_update = False
@@ -65,10 +92,7 @@ class Signal(object):
         self.wav_mode = filename.endswith(".wav")
         self.flipper_raw_mode = filename.endswith(".sub")
         self.__changed = False
-        self.__modulation_type = "FSK" if modulation is None else modulation
-        self.__bits_per_symbol = 1
-        self.__center_spacing = 1  # for higher order modulations
-        self.__parameter_cache = {mod: {"center": None, "samples_per_symbol": None} for mod in self.MODULATION_TYPES}
+        self.parameter_cache = {mod: {"center": None, "samples_per_symbol": None} for mod in self.MODULATION_TYPES}
         self.__already_demodulated = False
         self.filename = ""
         if len(filename) > 0:
@@ -150,36 +174,24 @@ class Signal(object):
         self.iq_array = IQArray.from_file(path)
         os.remove(path)
 
-    # ---- plain properties ---------------------------------------------------------------------------------------------
+    # ---- parameters (Signal.py:215-400) ----------------------------------------------------------------------------------
+    # changing modulation type / bits per symbol / Costas bandwidth invalidates the demodulated samples; everything
+    # but the name and the sample rate asks for a new protocol
+    name = _Tracked(update=False)
+    sample_rate = _Tracked(update=False)
+    modulation_type = _Tracked(drops_qad=True)
+    bits_per_symbol = _Tracked(cast=int, drops_qad=True)
+    samples_per_symbol = _Tracked()
+    tolerance = _Tracked(cast=int)
+    center = _Tracked()
+    center_spacing = _Tracked()
+    pause_threshold = _Tracked(event=False)
+    message_length_divisor = _Tracked(event=False)
+    costas_loop_bandwidth = _Tracked(event=False, drops_qad=True)
+
     @property
     def already_demodulated(self) -> bool:
         return self.__already_demodulated
-
-    @property
-    def sample_rate(self):
-        return self.__sample_rate
-
-    @sample_rate.setter
-    def sample_rate(self, val):
-        if val != self.sample_rate:
-            self.__sample_rate = val
-            self.sample_rate_changed.emit(val)
-
-    @property
-    def timestamp(self):
-        return self.__timestamp
-
-    @timestamp.setter
-    def timestamp(self, val):
-        self.__timestamp = val
-
-    @property
-    def parameter_cache(self) -> dict:
-        return self.__parameter_cache
-
-    @parameter_cache.setter
-    def parameter_cache(self, val):
-        self.__parameter_cache = val
 
     def _needs_update(self):
         if not self.block_protocol_update:
@@ -190,122 +202,12 @@ class Signal(object):
         self._qad_dev = None
 
     @property
-    def modulation_type(self) -> str:
-        return self.__modulation_type
-
-    @modulation_type.setter
-    def modulation_type(self, value: str):
-        if self.__modulation_type != value:
-            self.__modulation_type = value
-            self._drop_qad()
-            self.modulation_type_changed.emit(value)
-            self._needs_update()
-
-    @property
-    def bits_per_symbol(self):
-        return self.__bits_per_symbol
-
-    @bits_per_symbol.setter
-    def bits_per_symbol(self, value: int):
-        if self.__bits_per_symbol != value:
-            self.__bits_per_symbol = int(value)
-            self._drop_qad()
-            self.bits_per_symbol_changed.emit(self.__bits_per_symbol)
-            self._needs_update()
-
-    @property
-    def samples_per_symbol(self):
-        return self.__samples_per_symbol
-
-    @samples_per_symbol.setter
-    def samples_per_symbol(self, value):
-        if self.__samples_per_symbol != value:
-            self.__samples_per_symbol = value
-            self.samples_per_symbol_changed.emit(value)
-            self._needs_update()
-
-    @property
     def modulation_order(self):
         return 2 ** self.bits_per_symbol
 
     @property
-    def tolerance(self):
-        return self.__tolerance
-
-    @tolerance.setter
-    def tolerance(self, value):
-        value = int(value)
-        if self.__tolerance != value:
-            self.__tolerance = value
-            self.tolerance_changed.emit(value)
-            self._needs_update()
-
-    @property
-    def center(self):
-        return self.__center
-
-    @center.setter
-    def center(self, value: float):
-        if self.__center != value:
-            self.__center = value
-            self.center_changed.emit(value)
-            self._needs_update()
-
-    @property
-    def center_spacing(self) -> float:
-        return self.__center_spacing
-
-    @center_spacing.setter
-    def center_spacing(self, value: float):
-        if self.__center_spacing != value:
-            self.__center_spacing = value
-            self.center_spacing_changed.emit(value)
-            self._needs_update()
-
-    @property
     def center_thresholds(self):
         return self.get_thresholds_for_center(self.center)
-
-    @property
-    def pause_threshold(self) -> int:
-        return self.__pause_threshold
-
-    @pause_threshold.setter
-    def pause_threshold(self, value: int):
-        if self.__pause_threshold != value:
-            self.__pause_threshold = value
-            self._needs_update()
-
-    @property
-    def costas_loop_bandwidth(self):
-        return self.__costas_loop_bandwidth
-
-    @costas_loop_bandwidth.setter
-    def costas_loop_bandwidth(self, value: float):
-        if self.__costas_loop_bandwidth != value:
-            self.__costas_loop_bandwidth = value
-            self._drop_qad()
-            self._needs_update()
-
-    @property
-    def message_length_divisor(self) -> int:
-        return self.__message_length_divisor
-
-    @message_length_divisor.setter
-    def message_length_divisor(self, value: int):
-        if self.__message_length_divisor != value:
-            self.__message_length_divisor = value
-            self._needs_update()
-
-    @property
-    def name(self):
-        return self.__name
-
-    @name.setter
-    def name(self, value):
-        if value != self.__name:
-            self.__name = value
-            self.name_changed.emit(value)
 
     @property
     def num_samples(self):
@@ -421,9 +323,9 @@ class Signal(object):
         new_signal._noise_threshold = self.noise_threshold
         new_signal.noise_min_plot = self.noise_min_plot
         new_signal.noise_max_plot = self.noise_max_plot
-        new_signal._Signal__samples_per_symbol = self.samples_per_symbol
-        new_signal._Signal__bits_per_symbol = self.bits_per_symbol
-        new_signal._Signal__center = self.center
+        new_signal._p_samples_per_symbol = self.samples_per_symbol
+        new_signal._p_bits_per_symbol = self.bits_per_symbol
+        new_signal._p_center = self.center
         new_signal.wav_mode = self.wav_mode
         new_signal.flipper_raw_mode = self.flipper_raw_mode
         new_signal._Signal__already_demodulated = self.already_demodulated
@@ -491,7 +393,7 @@ class Signal(object):
         self.parameter_cache.clear()
 
     def silent_set_modulation_type(self, mod_type: str):
-        self.__modulation_type = mod_type
+        self._p_modulation_type = mod_type
 
     # ---- edit operations (Signal.py:613-651) --------------------------------------------------------------------------------
     def insert_data(self, index: int, data: np.ndarray):
