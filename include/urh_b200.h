@@ -142,6 +142,8 @@ int urh_fir_filter(urh_ctx* ctx, const float* d_x, int64_t n, const float* d_tap
 int urh_convolve_c128(urh_ctx* ctx, const float* d_x, int64_t n, const double* d_taps, int m, int64_t offset,
                       int64_t out_len, float* d_y);
 int urh_dc_correction(urh_ctx* ctx, const float* d_iq, int64_t n, float* d_out, int exact_order);
+/* the same for an integer capture: numpy promotes to float64 (exact integer column sums), d_out = double[n][2] */
+int urh_dc_correction_int(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, double* d_out);
 
 /* ---- spectrogram (spectrogram.cu; cuFFT for the FFT only) -------------------------------------------------
  * urh_stft replaces Spectrogram.stft (Spectrogram.py:94-116): complex128 [num_frames][window_size] = fft(frames*window)/W;

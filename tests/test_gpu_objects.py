@@ -313,3 +313,18 @@ def test_estimate_frequency_matches_numpy():
         s.iq_array = IQArray(x)
         w = np.fft.fft(x[:4096])
         assert s.estimate_frequency(0, 5000, 2e6) == abs(np.fft.fftfreq(4096)[np.argmax(np.abs(w))] * 2e6)
+
+
+@pytest.mark.parametrize("dtype", [np.int8, np.uint8, np.int16, np.uint16])
+def test_dc_correction_integer_capture_matches_numpy(dtype):
+    """integer captures: numpy promotes x - mean(x, axis=0) to float64; exact integer column sums -> bit-identical"""
+    from urh_b200.signalprocessing.Filter import Filter
+    rng = np.random.default_rng(3)
+    info = np.iinfo(dtype)
+    for n in (1, 7, 1000, 300_001):
+        x = rng.integers(info.min, info.max + 1, (n, 2)).astype(dtype)
+        x[:, 0] = np.clip(x[:, 0].astype(np.int64) // 2 + info.max // 3, info.min, info.max).astype(dtype)   # a DC offset
+        got = Filter.dc_correction(x)
+        ref = x - np.mean(x, axis=0)
+        assert got.dtype == np.float64 and got.shape == ref.shape
+        assert np.array_equal(got, ref), (dtype, n)

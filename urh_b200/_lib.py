@@ -94,6 +94,7 @@ SIGNATURES = {
     "urh_fir_filter": (i32, [vp, vp, i64, vp, i32, vp]),
     "urh_convolve_c128": (i32, [vp, vp, i64, vp, i32, i64, i64, vp]),
     "urh_dc_correction": (i32, [vp, vp, i64, vp, i32]),
+    "urh_dc_correction_int": (i32, [vp, vp, i32, i64, vp]),
     "urh_stft": (i32, [vp, vp, i64, i32, i32, vp, i64, vp]),
     "urh_spectrogram_db": (i32, [vp, vp, i64, i32, i32, vp, i64, vp]),
     "urh_shard_dense": (i32, [vp, vp, i32, i64, i32, f32, i32, f32, u16, u8, f32, vp, vp]),

@@ -288,3 +288,65 @@ extern "C" int urh_dc_correction(urh_ctx* ctx, const float* d_iq, int64_t n, flo
     URH_LAUNCH(ctx, k_dc_subtract, grid, 256, 0, (const float2*)d_iq, n, mean, (float2*)d_out);
     return URH_OK;
 }
+
+// ---- DC correction of an INTEGER capture: numpy promotes `x - np.mean(x, axis=0)` to float64; the column sums of integers
+// are exact (int64 here, float64 pairwise in numpy: both exact below 2^53), mean = sum / n in double, result double[n][2].
+template <typename T>
+__global__ void __launch_bounds__(256) k_dc_int_partial(const T* __restrict__ x, int64_t n, long long* __restrict__ part) {
+    long long sr = 0, si = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        sr += (long long)x[2 * i];
+        si += (long long)x[2 * i + 1];
+    }
+    __shared__ long long s_r[256], s_i[256];
+    s_r[threadIdx.x] = sr; s_i[threadIdx.x] = si;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) { s_r[threadIdx.x] += s_r[threadIdx.x + off]; s_i[threadIdx.x] += s_i[threadIdx.x + off]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = s_r[0]; part[2 * blockIdx.x + 1] = s_i[0]; }
+}
+__global__ void k_dc_int_fold(const long long* __restrict__ part, int nblocks, int64_t n, double* __restrict__ mean) {
+    if (threadIdx.x < 2) {
+        long long s = 0;
+        for (int b = 0; b < nblocks; b++) s += part[2 * b + threadIdx.x];
+        mean[threadIdx.x] = __ddiv_rn((double)s, (double)n);
+    }
+}
+template <typename T>
+__global__ void k_dc_int_subtract(const T* __restrict__ x, int64_t n, const double* __restrict__ mean, double* __restrict__ y) {
+    const double mr = mean[0], mi = mean[1];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        y[2 * i] = __dsub_rn((double)x[2 * i], mr);
+        y[2 * i + 1] = __dsub_rn((double)x[2 * i + 1], mi);
+    }
+}
+
+template <typename T>
+static int dc_int(urh_ctx* ctx, const void* d_iq, int64_t n, double* d_out) {
+    const int nb = ctx->sm_count * 4;
+    long long* part;
+    double* mean;
+    URH_CHECK(urh_arena(ctx, (size_t)nb * 2, &part));
+    URH_CHECK(urh_arena(ctx, 2, &mean));
+    URH_LAUNCH(ctx, k_dc_int_partial<T>, nb, 256, 0, (const T*)d_iq, n, part);
+    URH_LAUNCH(ctx, k_dc_int_fold, 1, 32, 0, (const long long*)part, nb, n, mean);
+    const unsigned grid = (unsigned)min(urh_div_up(n, 256), (int64_t)ctx->sm_count * 16);
+    URH_LAUNCH(ctx, k_dc_int_subtract<T>, grid, 256, 0, (const T*)d_iq, n, (const double*)mean, d_out);
+    return URH_OK;
+}
+
+extern "C" int urh_dc_correction_int(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, double* d_out) {
+    if (n <= 0) return URH_OK;
+    urh_arena_reset(ctx);
+    switch (dtype) {
+        case URH_DT_I8: return dc_int<int8_t>(ctx, d_iq, n, d_out);
+        case URH_DT_U8: return dc_int<uint8_t>(ctx, d_iq, n, d_out);
+        case URH_DT_I16: return dc_int<int16_t>(ctx, d_iq, n, d_out);
+        case URH_DT_U16: return dc_int<uint16_t>(ctx, d_iq, n, d_out);
+        default: URH_FAIL(ctx, URH_ERR_DTYPE, "urh_dc_correction_int: integer capture expected");
+    }
+}

@@ -35,9 +35,18 @@ class Filter(object):
     @staticmethod
     def dc_correction(input_signal: np.ndarray) -> np.ndarray:
         """input_signal - np.mean(input_signal, axis=0) (Filter.py:32-33)"""
+        ctx = _lib.default_context()
         if input_signal.dtype != np.float32:
-            # integer captures: numpy promotes to float64 and the mean of integers is exact in double
-            return input_signal - np.mean(input_signal, axis=0)
+            # integer captures: numpy promotes to float64 and the column means of integers are exact in double
+            x = np.ascontiguousarray(input_signal)
+            if x.dtype not in (np.int8, np.uint8, np.int16, np.uint16) or x.ndim != 2 or x.shape[1] != 2:
+                raise ValueError("dc_correction expects an (n, 2) capture of int8/uint8/int16/uint16/float32")
+            if len(x) == 0:
+                return x.astype(np.float64)
+            d = to_device(x, ctx)
+            out = DeviceArray(ctx, x.shape, np.float64)
+            ctx.check(ctx.lib.urh_dc_correction_int(ctx.handle, C.c_void_p(d.ptr), _lib.dtype_code(x.dtype), len(x), C.c_void_p(out.ptr)))
+            return out.get()
         ctx = _lib.default_context()
         x = np.ascontiguousarray(input_signal)
         n = len(x)
