@@ -1,0 +1,129 @@
+"""CPU: the host-side logic of the drop-in layer against the REFERENCE's own functions on randomized inputs (the reference
+is imported through oracle/ref_loader.py; skipped where /root/reference does not exist).  These functions never touch the
+GPU: pulses -> bits, plateau / bit-length bookkeeping of estimate(), modulator parameter preparation, filter design,
+bit utilities."""
+import array
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/src/urh"), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_loader
+    ns = ref_loader.load_python_layer()
+    sf, ut, ai = ref_loader.load_kernels()
+    ns.sf, ns.ut, ns.ai = sf, ut, ai
+    return ns
+
+
+def test_ppseq_to_bits_port(ref):
+    from urh_b200.signalprocessing.ProtocolAnalyzer import ProtocolAnalyzer as PA
+    rfun = ref.ProtocolAnalyzer(None)._ppseq_to_bits   # an instance method in the reference (ProtocolAnalyzer.py:323)
+    rng = np.random.default_rng(5)
+    for trial in range(300):
+        bps = int(rng.choice([1, 2]))
+        pt = int(rng.choice([8, 0, 2]))
+        sps = int(rng.choice([1, 3, 10, 100]))
+        k = int(rng.integers(1, 80))
+        kinds = rng.integers(-1, 1 << bps, k)
+        ns = np.where(rng.random(k) < 0.15, rng.integers(9, 30, k) * sps, rng.integers(0, 5 * sps + 1, k))
+        rows = np.stack([kinds, ns], axis=1).astype(np.int64)
+        wp = bool(trial % 2)
+        mine = PA._ppseq_to_bits(rows, sps, bps, write_bit_sample_pos=wp, pause_threshold=pt)
+        theirs = rfun(rows, sps, bps, write_bit_sample_pos=wp, pause_threshold=pt)
+        assert [list(x) for x in mine[0]] == [list(x) for x in theirs[0]], trial
+        assert list(mine[1]) == list(theirs[1]), trial
+        assert [list(x) for x in mine[2]] == [list(x) for x in theirs[2]], trial
+
+
+def test_plateau_bookkeeping(ref):
+    from urh_b200.ainterpretation import AutoInterpretation as AI
+    R = ref.AutoInterpretation
+    rng = np.random.default_rng(9)
+    for trial in range(300):
+        n = int(rng.integers(2, 60))
+        base = int(rng.choice([8, 40, 100, 300]))
+        pl = (rng.integers(1, 6, n) * base + rng.integers(-base // 8 - 1, base // 8 + 2, n)).clip(1)
+        if trial % 3 == 0:
+            pl[rng.integers(0, n, max(1, n // 6))] = rng.integers(1, 4, max(1, n // 6))   # tiny glitches
+        pl = pl.astype(np.uint64)
+        assert AI.estimate_tolerance_from_plateau_lengths(pl) == R.estimate_tolerance_from_plateau_lengths(pl), trial
+        for tol in (None, 0, 1, 3):
+            assert list(AI.merge_plateau_lengths(pl, tolerance=tol)) == list(R.merge_plateau_lengths(pl, tolerance=tol)), (trial, tol)
+        merged = R.merge_plateau_lengths(pl)
+        if len(merged) >= 2:
+            assert AI.get_bit_length_from_plateau_lengths(merged) == R.get_bit_length_from_plateau_lengths(merged), trial
+        a, b = [int(v) for v in pl], [int(v) for v in pl]
+        AI.round_plateau_lengths(a)       # in place
+        R.round_plateau_lengths(b)
+        assert a == b, trial
+        assert AI.get_tolerant_greatest_common_divisor(list(pl)) == R.get_tolerant_greatest_common_divisor(list(pl)), trial
+        vals = [int(v) for v in rng.integers(0, 6, n)]
+        assert AI.get_most_frequent_value(vals) == R.get_most_frequent_value(vals)
+        data = rng.standard_normal(n + 3) * 10 + 50
+        assert AI.max_without_outliers(data) == R.max_without_outliers(data)
+        assert AI.min_without_outliers(data) == R.min_without_outliers(data)
+
+
+def test_cython_host_helpers(ref):
+    from urh_b200.cythonext import auto_interpretation as cai, signal_functions as sf, util
+    rng = np.random.default_rng(2)
+    for trial in range(200):
+        n = int(rng.integers(1, 80))
+        pl = rng.integers(1, 400, n).astype(np.uint64)
+        tol, mc = int(rng.integers(0, 12)), int(rng.integers(1, 40))
+        assert list(cai.merge_plateaus(pl, tol, mc)) == list(np.asarray(ref.ai.merge_plateaus(pl, tol, mc))), trial
+        assert list(cai.get_threshold_divisor_histogram(pl)) == list(np.asarray(ref.ai.get_threshold_divisor_histogram(pl))), trial
+        bits = rng.integers(0, 2, int(rng.integers(0, 40))).astype(np.uint8)
+        assert list(sf.get_oqpsk_bits(bits)) == list(np.asarray(ref.sf.get_oqpsk_bits(bits))), trial
+        if len(bits):
+            a, b = sorted(rng.integers(0, len(bits) + 1, 2))
+            assert util.bit_array_to_number(bits, int(b), int(a)) == ref.ut.bit_array_to_number(bits, int(b), int(a))
+    for sr, sps, bt, fw in ((2e6, 100, 0.5, 1.0), (1e6, 8, 0.3, 1.5), (250e3, 33, 1.0, 0.7)):
+        mine = sf.gauss_fir(sr, sps, bt, fw)
+        theirs = np.asarray(ref.sf.get_gauss_fir(sr, sps, bt, fw)) if hasattr(ref.sf, "get_gauss_fir") else None
+        if theirs is not None:
+            assert np.array_equal(mine, theirs)
+
+
+def test_modulator_and_filter_host_logic(ref):
+    from urh_b200.signalprocessing.Filter import Filter
+    from urh_b200.signalprocessing.Modulator import Modulator
+    for bw in (0.001, 0.04, 0.08, 0.42):
+        assert Filter.get_filter_length_from_bandwidth(bw) == ref.Filter.get_filter_length_from_bandwidth(bw)
+        N = Filter.get_filter_length_from_bandwidth(bw)
+        assert Filter.get_bandwidth_from_filter_length(N) == ref.Filter.get_bandwidth_from_filter_length(N)
+        if N < 2000:
+            assert np.array_equal(Filter.design_windowed_sinc_lpf(0.1, bw), ref.Filter.design_windowed_sinc_lpf(0.1, bw))
+            assert np.array_equal(Filter.design_windowed_sinc_bandpass(-0.1, 0.2, bw), ref.Filter.design_windowed_sinc_bandpass(-0.1, 0.2, bw))
+    for mod in ("ASK", "FSK", "PSK", "GFSK", "OQPSK"):
+        for bps in ((1, 2, 3) if mod != "OQPSK" else (2,)):
+            m, r = Modulator("m"), ref.Modulator("m")
+            for o in (m, r):
+                o.modulation_type = mod
+                o.bits_per_symbol = bps
+                o.sample_rate = 2e6
+            assert list(m.get_default_parameters()) == list(r.get_default_parameters()), (mod, bps)
+            assert m.modulation_order == r.modulation_order and m.is_binary_modulation == r.is_binary_modulation
+            assert (m.is_amplitude_based, m.is_frequency_based, m.is_phase_based) == (r.is_amplitude_based, r.is_frequency_based, r.is_phase_based)
+
+
+def test_iq_array_host_logic(ref):
+    from urh_b200.signalprocessing.IQArray import IQArray
+    rng = np.random.default_rng(4)
+    for dt in (np.int8, np.uint8, np.int16, np.uint16, np.float32):
+        assert IQArray.min_max_for_dtype(dt) == ref.IQArray.min_max_for_dtype(dt)
+    c = (rng.standard_normal(10) + 1j * rng.standard_normal(10)).astype(np.complex64)
+    for arr in (c, c.astype(np.complex128), rng.standard_normal(20).astype(np.float32), rng.integers(-100, 100, (10, 2)).astype(np.int16),
+                rng.integers(0, 255, 20).astype(np.uint8)):
+        assert np.array_equal(IQArray.convert_array_to_iq(arr), ref.IQArray.convert_array_to_iq(arr))
+        a, b = IQArray(arr), ref.IQArray(arr)
+        assert a.num_samples == b.num_samples and a.dtype == b.dtype and a.minimum == b.minimum and a.maximum == b.maximum
+        assert np.array_equal(a.real, b.real) and np.array_equal(a.imag, b.imag)
+    for name in ("x.complex", "x.cs8", "x.complex16u", "x.cu16", "x.complex32s", "x.wav"):
+        exp = {"x.complex": np.float32, "x.cs8": np.int8, "x.complex16u": np.uint8, "x.cu16": np.uint16, "x.complex32s": np.int16, "x.wav": np.float32}[name]
+        assert IQArray._dtype_for_filename(name) == exp
