@@ -81,3 +81,37 @@ def test_construction_defaults_match_reference():
                      "already_demodulated", "modulation_order"):
             assert getattr(mine, attr) == getattr(ref, attr), attr
         assert mine.parameter_cache == ref.parameter_cache
+
+
+def test_edit_operations_match_reference():
+    """insert / delete / mute / crop (Signal.py:613-651) on host data: same samples, same cached demodulation, same flags"""
+    from oracle import ref_loader
+    ns = ref_loader.load_python_layer()
+    from urh_b200.signalprocessing.Signal import Signal
+
+    rng = np.random.default_rng(8)
+    for trial in range(20):
+        n = int(rng.integers(20, 200))
+        iq = rng.integers(-100, 100, (n, 2)).astype(np.int16) if trial % 2 else rng.standard_normal((n, 2)).astype(np.float32)
+        mine, ref = Signal.from_samples(iq.copy(), "e", 1e6), ns.Signal.from_samples(iq.copy(), "e", 1e6)
+        qad = rng.standard_normal(n).astype(np.float32)
+        for s in (mine, ref):
+            s._qad = qad.copy()
+            s.parameter_cache["FSK"]["center"] = 0.5
+        a, b = sorted(int(v) for v in rng.integers(0, n, 2))
+        op = trial % 4
+        for s in (mine, ref):
+            if op == 0:
+                s.mute_range(a, b)
+            elif op == 1:
+                s.delete_range(a, b)
+            elif op == 2:
+                s.crop_to_range(a, max(b, a + 1))
+            else:
+                s.insert_data(a, iq[:5].copy())
+        assert np.array_equal(mine.iq_array.data, ref.iq_array.data), (trial, op)
+        assert (mine._qad is None) == (ref._qad is None), (trial, op)
+        if mine._qad is not None:
+            assert np.array_equal(mine._qad, ref._qad), (trial, op)
+        assert mine.changed == ref.changed and mine.num_samples == ref.num_samples
+        assert mine.parameter_cache == ref.parameter_cache
