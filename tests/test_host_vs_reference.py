@@ -127,3 +127,33 @@ def test_iq_array_host_logic(ref):
     for name in ("x.complex", "x.cs8", "x.complex16u", "x.cu16", "x.complex32s", "x.wav"):
         exp = {"x.complex": np.float32, "x.cs8": np.int8, "x.complex16u": np.uint8, "x.cu16": np.uint16, "x.complex32s": np.int16, "x.wav": np.float32}[name]
         assert IQArray._dtype_for_filename(name) == exp
+
+
+def test_ring_buffer(ref):
+    """util/RingBuffer.py:7-140: push / pop / wrap-around / clear on randomized traffic"""
+    import importlib
+    from urh_b200.util.RingBuffer import RingBuffer
+    RRing = importlib.import_module("urh.util.RingBuffer").RingBuffer
+    from urh_b200.signalprocessing.IQArray import IQArray
+    rng = np.random.default_rng(6)
+    for dtype in (np.float32, np.int8):
+        mine, theirs = RingBuffer(size=64, dtype=dtype), RRing(size=64, dtype=dtype)
+        for step in range(300):
+            if rng.random() < 0.55:
+                k = int(rng.integers(1, 40))
+                vals = (rng.standard_normal((k, 2)) * 50).astype(dtype)
+                assert mine.will_fit(k) == theirs.will_fit(k)
+                if mine.will_fit(k):
+                    mine.push(IQArray(vals.copy()))
+                    theirs.push(ref.IQArray(vals.copy()))
+            else:
+                k = int(rng.integers(1, 50))
+                even = bool(step % 2)
+                a, b = mine.pop(k, ensure_even_length=even), theirs.pop(k, ensure_even_length=even)
+                assert np.array_equal(np.asarray(a), np.asarray(b)), (dtype, step)
+            assert (mine.left_index, mine.right_index, mine.space_left, mine.is_empty, len(mine)) == \
+                   (theirs.left_index, theirs.right_index, theirs.space_left, theirs.is_empty, len(theirs))
+            assert np.array_equal(np.asarray(mine.view_data), np.asarray(theirs.view_data))
+            if step % 97 == 0:
+                mine.clear()
+                theirs.clear()
