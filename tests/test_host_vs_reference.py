@@ -157,3 +157,45 @@ def test_ring_buffer(ref):
             if step % 97 == 0:
                 mine.clear()
                 theirs.clear()
+
+
+def test_modulator_prepares_the_same_kernel_call(ref, monkeypatch):
+    """Modulator.modulate (Modulator.py:215-255): the arguments handed to modulate_c are the reference's (both kernels are
+    replaced by recorders here, so no GPU and no Cython code runs)"""
+    import importlib
+    import urh_b200.signalprocessing.Modulator as mine_mod
+    ref_mod = importlib.import_module("urh.signalprocessing.Modulator")
+    calls = {"mine": [], "ref": []}
+
+    def recorder(key):
+        def fake(bits, sps, mod_type, parameters, bps, a, f, phi, sr, pause, start, dtype=np.float32, gauss_bt=0.5, filter_width=1.0):
+            calls[key].append((list(bits), sps, mod_type, [float(p) for p in parameters], bps, float(a), float(f), float(phi), float(sr),
+                               pause, start, np.dtype(dtype), float(gauss_bt), float(filter_width)))
+            total = (len(bits) // bps) * sps + pause
+            return np.zeros((total, 2), dtype=dtype)
+        return fake
+
+    monkeypatch.setattr(mine_mod.signal_functions, "modulate_c", recorder("mine"))
+    monkeypatch.setattr(ref_mod.signal_functions, "modulate_c", recorder("ref"))
+    rng = np.random.default_rng(12)
+    for mod in ("ASK", "FSK", "PSK", "GFSK"):
+        for trial in range(6):
+            m, r = mine_mod.Modulator("t"), ref_mod.Modulator("t")
+            bps = int(rng.choice([1, 2]))
+            cfg = dict(modulation_type=mod, bits_per_symbol=bps, samples_per_symbol=int(rng.choice([8, 100])), sample_rate=float(rng.choice([1e6, 2e6])),
+                       carrier_freq_hz=float(rng.choice([0.0, 20e3])), carrier_amplitude=float(rng.choice([1.0, 0.5])),
+                       carrier_phase_deg=float(rng.choice([0.0, 45.0])), gauss_bt=0.5, gauss_filter_width=1.0)
+            for o in (m, r):
+                for k_, v in cfg.items():
+                    setattr(o, k_, v)
+                o.parameters = o.get_default_parameters()
+            nbits = int(rng.integers(0, 12)) * bps
+            data = [int(b) for b in rng.integers(0, 2, nbits)]
+            payload = "".join(map(str, data)) if trial % 2 else list(data)
+            pause, start = int(rng.integers(0, 50)), int(rng.integers(0, 1000))
+            dtype = [None, np.int8, np.int16, np.float32][trial % 4]
+            a = m.modulate(payload, pause=pause, start=start, dtype=dtype)
+            b = r.modulate(payload, pause=pause, start=start, dtype=dtype)
+            assert a.data.shape == b.data.shape and a.dtype == b.dtype
+    assert len(calls["mine"]) == len(calls["ref"]) > 0
+    assert calls["mine"] == calls["ref"]
