@@ -199,3 +199,18 @@ def test_modulator_prepares_the_same_kernel_call(ref, monkeypatch):
             assert a.data.shape == b.data.shape and a.dtype == b.dtype
     assert len(calls["mine"]) == len(calls["ref"]) > 0
     assert calls["mine"] == calls["ref"]
+
+
+def test_spectrogram_geometry(ref):
+    """Spectrogram.py:84-103: hop size, bin counts and the number of STFT frames (the reference's frame count is the
+    shape of its strided view; ours is computed up front to size the device buffers)"""
+    from urh_b200.signalprocessing.Spectrogram import Spectrogram
+    rng = np.random.default_rng(1)
+    for trial in range(40):
+        n = int(rng.integers(1, 5000))
+        w = int(rng.choice([16, 64, 256, 1024]))
+        ov = float(rng.choice([0.5, 0.0, 0.75, 0.3]))
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        a, b = Spectrogram(x, window_size=w, overlap_factor=ov), ref.Spectrogram(x, window_size=w, overlap_factor=ov)
+        assert (a.hop_size, a.time_bins, a.freq_bins) == (b.hop_size, b.time_bins, b.freq_bins)
+        assert a._num_frames(n) == b.stft(x).shape[0], (n, w, ov)
