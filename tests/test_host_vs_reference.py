@@ -214,3 +214,20 @@ def test_spectrogram_geometry(ref):
         a, b = Spectrogram(x, window_size=w, overlap_factor=ov), ref.Spectrogram(x, window_size=w, overlap_factor=ov)
         assert (a.hop_size, a.time_bins, a.freq_bins) == (b.hop_size, b.time_bins, b.freq_bins)
         assert a._num_frames(n) == b.stft(x).shape[0], (n, w, ov)
+
+
+def test_merge_message_segments_for_ook(ref):
+    from urh_b200.ainterpretation import AutoInterpretation as AI
+    rng = np.random.default_rng(21)
+    assert AI.merge_message_segments_for_ook([]) == ref.AutoInterpretation.merge_message_segments_for_ook([])
+    for trial in range(300):
+        k = int(rng.integers(1, 25))
+        pos = 0
+        segs = []
+        pulse = int(rng.choice([20, 100, 400]))
+        for _ in range(k):
+            pos += int(rng.choice([pulse // 2, pulse, 3 * pulse, 9 * pulse, 40 * pulse])) + int(rng.integers(0, 5))
+            length = int(rng.integers(1, 4)) * pulse + int(rng.integers(0, 7))
+            segs.append((pos, pos + length))
+            pos += length
+        assert AI.merge_message_segments_for_ook(list(segs)) == ref.AutoInterpretation.merge_message_segments_for_ook(list(segs)), trial
