@@ -231,3 +231,29 @@ def test_merge_message_segments_for_ook(ref):
             segs.append((pos, pos + length))
             pos += length
         assert AI.merge_message_segments_for_ook(list(segs)) == ref.AutoInterpretation.merge_message_segments_for_ook(list(segs)), trial
+
+
+def test_noise_level_decision_from_chunk_statistics(ref):
+    """detect_noise_level (AutoInterpretation.py:60-91): the device only delivers (sum, max) of the 100 end-aligned
+    chunks; here they come from numpy, the decision logic is ours, the expected value is the reference's."""
+    from urh_b200.ainterpretation import AutoInterpretation as AI
+    rng = np.random.default_rng(14)
+    for trial in range(200):
+        n = int(rng.integers(4, 40000))
+        dtype = np.float64 if trial % 2 else np.float32
+        mags = np.abs(rng.standard_normal(n) * 0.01)
+        kind = trial % 5
+        if kind < 3:
+            a = int(rng.integers(0, n))
+            mags[a: a + n // 3] += rng.uniform(0.3, 1.0)          # a burst
+        elif kind == 3:
+            mags += 0.5                                            # signal everywhere: chunk means nearly equal -> 0
+        else:
+            mags[:] = 0.0
+        mags = mags.astype(dtype)
+        chunksize, nchunks = AI._chunking(n)
+        tail = mags[n - nchunks * chunksize:].reshape(nchunks, chunksize)   # chunks are taken from the end backwards
+        sums = tail.astype(np.float64).sum(axis=1)
+        maxs = tail.max(axis=1).astype(np.float64)
+        got = AI._noise_from_chunk_stats(n, chunksize, sums, maxs, dtype)
+        assert got == ref.AutoInterpretation.detect_noise_level(mags), (trial, n)
