@@ -184,9 +184,10 @@ def main():
     local_rank = env_int("LOCAL_RANK", 0)
     world = env_int("WORLD_SIZE", 1)
     n = 1 << args.log2n
-    workload = ("2-FSK complex64, ONE capture of %d x 2^%d samples sharded by contiguous range (1-sample halo, NCCL run stitching) "
-                "@2MS/s sps=100 +-100kHz AWGN sigma=0.01 bursts+gaps; %s (tol=5, noise=0.05)"
-                % (world, args.log2n, "demod + detect_center (capture-wide) + digitize" if args.center == "detect"
+    layout = ("2^%d samples on one GPU" % args.log2n if world == 1 else
+              "ONE capture of %d x 2^%d samples sharded by contiguous range (1-sample halo, NCCL run stitching)" % (world, args.log2n))
+    workload = ("2-FSK complex64, %s @2MS/s sps=100 +-100kHz AWGN sigma=0.01 bursts+gaps; %s (tol=5, noise=0.05)"
+                % (layout, "demod + detect_center (capture-wide) + digitize" if args.center == "detect"
                    else "fused demod+digitize, center=0 given"))
     base = {"metric": "MSamples/s IQ demod+digitize (complex64)", "unit": "MSamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
