@@ -257,3 +257,21 @@ def test_noise_level_decision_from_chunk_statistics(ref):
         maxs = tail.max(axis=1).astype(np.float64)
         got = AI._noise_from_chunk_stats(n, chunksize, sums, maxs, dtype)
         assert got == ref.AutoInterpretation.detect_noise_level(mags), (trial, n)
+
+
+def test_oracle_convert_iq_is_the_references_convert_to(ref, oracle):
+    """closes the chain for the format conversions: reference IQArray.convert_to == oracle.convert_iq (here) == convert.cu
+    (tests/test_gpu_objects.py::test_convert_to_all_pairs)"""
+    rng = np.random.default_rng(5)
+    types = [np.int8, np.uint8, np.int16, np.uint16, np.float32]
+    for src in types:
+        if src == np.float32:
+            x = np.concatenate([rng.uniform(-1, 1, 4000), [-1.0, 1.0, 0.0, -0.0, 0.999999, -0.999999]]).astype(np.float32)
+        else:
+            info = np.iinfo(src)
+            x = np.concatenate([rng.integers(info.min, info.max + 1, 4000), [info.min, info.max, 0, 1]]).astype(src)
+        x = np.ascontiguousarray(x.reshape(-1, 2))
+        for dst in types:
+            a = oracle.convert_iq(x, dst)
+            b = ref.IQArray(x).convert_to(dst)
+            assert a.dtype == b.dtype and np.array_equal(a.view(np.uint8), b.view(np.uint8)), (src, dst)
