@@ -1,14 +1,18 @@
 #!/usr/bin/env python
-"""bench.py — FSK demod + digitize of a synthetic 1 GiSample complex64 capture per B200 (BASELINE.json configs[1]).
+"""bench.py — FSK demod + center + digitize of a synthetic 1 GiSample complex64 capture per B200 (BASELINE.json configs[1]).
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the reference's own kernels)
 
-One "step" = one pass of the hot path over one capture shard resident in HBM:
-    urh_demod_digitize  (afp_demod FSK + grab_pulse_lens fused, qad materialised)  -> pulse table.
-`value` = whole-job MSamples/s with the IQ already in HBM; `e2e` = the same call fed from pinned HOST
-memory through the public Python API (H2D of the IQ and D2H of the pulse table inside the timed region).
-The capture (8 GiB / GPU) is far larger than the 126 MB L2, so no explicit L2 flush is needed.
+One "step" (default --center detect) = ONE library call per GPU, urh_demod_center_digitize (N>1:
+urh_shard_demod_center_digitize): afp_demod FSK with per-tile statistics -> capture-wide detect_center (rank window, bin
+edges, histogram, peak pick: all on the device) -> grab_pulse_lens over qad -> pulse table; the host synchronises once.
+--center given: the fused single-pass step for a known center (urh_demod_digitize / urh_shard_digitize), reported as
+`other_variant` otherwise.
+`value` = whole-job MSamples/s with the IQ already in HBM; `e2e` = the same step fed from pinned HOST memory through the
+public Python API (H2D of the IQ and D2H of the pulse table inside the timed region).  The capture (8 GiB / GPU) is far
+larger than the 126 MB L2, so no explicit L2 flush is needed.
+After the timed loops every run checks itself against the CPU oracle (outside the timed region): `parity` in the JSON line.
 """
 import argparse
 import ctypes as C
@@ -35,11 +39,13 @@ NOISE_MAG = 0.05
 SIGMA = 0.01
 TOL = 5
 CENTER = 0.0
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per sample, from the ncu --set full captures in profiles/
-# (taken at 2^28 samples; the kernels stream, so DRAM bytes scale with n)
-TRAFFIC_B_PER_SAMPLE = {"detect": (2.147530e9 + 1.026364e9) / (1 << 28), "given": (2.152927e9 + 1.030241e9) / (1 << 28)}
-TRAFFIC_SOURCE = "profiles/r01_ncu_detect_m_summary.txt / r01_ncu_fast_g_summary.txt (ncu --set full at 2^28 samples, scaled by n)"
-ALG_BYTES_PER_SAMPLE = 12  # read IQ 8 B + write qad 4 B (pulse table ~0.1 B/sample ignored)
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel: read at run time from the committed summary of this
+# round's `ncu --set full` capture (tools/ncu_summary.py writes profiles/traffic.json: bytes per sample per kernel, captured at
+# 2^28 samples; the kernels stream, so DRAM bytes scale with n).  null when the file is missing.
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")
+ALG_BYTES_PER_SAMPLE = 12  # dominant kernel, SURVEY §8d: read IQ 8 B + write qad 4 B (pulse table ~0.1 B/sample ignored)
+STEP_BYTES_PER_SAMPLE = {"detect": 16, "given": 12}  # SURVEY §8d per-path budgets (detect: qad re-read once)
+PARITY_LOG2 = 24  # parity windows of 2^24 samples (first / middle / last of every shard)
 
 
 def env_int(name, default):
@@ -109,9 +115,20 @@ class ClockSampler:
         return out
 
 
+def _reference_detect_center():
+    """the reference's own detect_center (numpy code, AutoInterpretation.py:226-277) when its Python layer travelled
+    with oracle/_ref (oracle/build_ref.py stages it), else the oracle's restatement of it"""
+    from oracle import oracle, ref_loader
+    try:
+        ns = ref_loader.load_python_layer()
+        return ns.AutoInterpretation.detect_center, "reference"
+    except Exception:
+        return oracle.detect_center, "port"
+
+
 def cpu_reference_arm(n_cpu, steps, warmup, iq_slice=None, detect=True):
     """Time the reference's own CPU implementation (oracle/_ref compiled from /root/reference if it travelled
-    here, else the C oracle port) of afp_demod(FSK) + grab_pulse_lens on a bounded slice, all host threads."""
+    here, else the C oracle port) of afp_demod(FSK) [+ detect_center] + grab_pulse_lens on a bounded slice, all host threads."""
     from oracle import oracle, ref_loader
 
     cores = os.cpu_count() or 1
@@ -129,6 +146,7 @@ def cpu_reference_arm(n_cpu, steps, warmup, iq_slice=None, detect=True):
         kind = "reference"
     except Exception:
         oracle.build()
+    detect_center, center_kind = _reference_detect_center()
     if iq_slice is None:
         iq_slice = host_synth(n_cpu)
     n_cpu = len(iq_slice)
@@ -137,16 +155,15 @@ def cpu_reference_arm(n_cpu, steps, warmup, iq_slice=None, detect=True):
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         q = demod(iq_slice, NOISE_MAG, "FSK", 2)
-        # detect_center is numpy code in the reference (AutoInterpretation.py:226-290); oracle.detect_center restates it
-        center = oracle.detect_center(q) if detect else CENTER
+        center = detect_center(q) if detect else CENTER
         rows = grab(q, center, TOL, "FSK", SPS)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    sec = float(np.mean(times))
+    sec = float(np.median(times))
     return {"value": n_cpu / sec / 1e6, "unit": "MSamples/s", "cores": cores, "kind": kind,
-            "sample": "%d-sample slice of the same synthetic 2-FSK capture (afp_demod FSK%s + grab_pulse_lens), mean of %d"
-                      % (n_cpu, " + detect_center (numpy, as in the reference)" if detect else "", len(times)),
+            "sample": "%d-sample slice of the same synthetic 2-FSK recipe (afp_demod FSK [%s]%s + grab_pulse_lens [%s]), median of %d"
+                      % (n_cpu, kind, (" + detect_center [%s, numpy as in the reference]" % center_kind) if detect else "", kind, len(times)),
             "ms_per_step": sec * 1e3, "rows": int(len(rows))}
 
 
@@ -166,6 +183,85 @@ def host_synth(n, seed=0):
     return iq
 
 
+def parity_windows(n_local):
+    w = min(n_local, 1 << PARITY_LOG2)
+    starts = sorted({0, ((n_local // 2) // 2048) * 2048 if n_local // 2 + w <= n_local else 0, n_local - w})
+    return w, starts
+
+
+def parity_block(ctx, rank, world, dist, d_iq, halo_host, d_qad, rows, center, n, n_total, offset):
+    """GPU result of the last timed step vs the CPU oracle (oracle/_ref = the reference's compiled kernels when they
+    travelled, else the C restatement), outside the timed region, on the first / middle / last 2^24 samples of this rank's
+    shard: every qad word, and every pulse boundary (position, state) of the WHOLE-capture pulse table that falls inside the
+    window (minus a margin in which a digitizer started at the window edge has not yet seen two runs)."""
+    from oracle import oracle, ref_loader
+
+    kind = "port"
+    demod, grab = oracle.afp_demod, oracle.grab_pulse_lens
+    try:
+        sfr, _, _ = ref_loader.load_kernels()
+        demod = lambda iq, nm, mt, mo: np.asarray(sfr.afp_demod(iq, nm, mt, mo))  # noqa: E731
+        grab = lambda q, c, t, mt, sps: np.asarray(sfr.grab_pulse_lens(q, c, t, mt, sps))  # noqa: E731
+        kind = "reference"
+    except Exception:
+        oracle.build()
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    # absolute position of the firing that ends row j: tol - 1 + (sum of all lengths up to and including row j)
+    s_local = int(rows[:, 1].sum())
+    before = 0
+    if dist is not None:
+        import torch
+
+        allv = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(allv, torch.tensor([s_local], dtype=torch.int64))
+        before = int(sum(int(v.item()) for v in allv[:rank]))
+    fire_rows = rows[:-1] if rank == world - 1 else rows   # the capture's last row is the tail row, not a firing
+    pos_gpu = TOL - 1 + before + np.cumsum(fire_rows[:, 1])
+    st_gpu = fire_rows[:, 0]
+    w, starts = parity_windows(n)
+    margin = min(w // 4, 1 << 21)
+    out = {"oracle": kind, "window_samples": w, "windows": len(starts), "qad_words_compared": 0, "qad_words_differing": 0,
+           "boundaries_compared": 0, "boundaries_differing": 0}
+    for a in starts:
+        # one predecessor sample for the FSK conjugate product (the halo for the shard's first sample)
+        if a > 0:
+            iq = d_iq[a - 1: a + w].get()
+        elif rank > 0:
+            iq = np.concatenate([halo_host, d_iq[0: w].get()])
+        else:
+            iq = d_iq[0: w].get()
+        q_ref = demod(np.ascontiguousarray(iq), NOISE_MAG, "FSK", 2)
+        if a > 0 or rank > 0:
+            q_ref = q_ref[1:]
+        q_gpu = d_qad[a: a + w].get()
+        out["qad_words_compared"] += int(w)
+        out["qad_words_differing"] += int(np.count_nonzero(q_gpu.view(np.uint32) != q_ref.view(np.uint32)))
+        r_ref = grab(np.ascontiguousarray(q_ref), float(center), TOL, "FSK", SPS)
+        g0 = offset + a
+        pos_ref = g0 + TOL - 1 + np.cumsum(r_ref[:-1, 1])
+        st_ref = r_ref[:-1, 0]
+        lo, hi = g0 + margin, g0 + w
+        mg = (pos_gpu > lo) & (pos_gpu < hi)
+        mr = (pos_ref > lo) & (pos_ref < hi)
+        pg, sg, pr, sr = pos_gpu[mg], st_gpu[mg], pos_ref[mr], st_ref[mr]
+        out["boundaries_compared"] += int(len(pr))
+        if len(pg) != len(pr):
+            out["boundaries_differing"] += abs(len(pg) - len(pr)) + 1
+        else:
+            out["boundaries_differing"] += int(np.count_nonzero((pg != pr) | (sg != sr)))
+    if dist is not None:
+        import torch
+
+        keys = ("qad_words_compared", "qad_words_differing", "boundaries_compared", "boundaries_differing")
+        t = torch.tensor([out[k_] for k_ in keys], dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        for k_, v in zip(keys, t.tolist()):
+            out[k_] = int(v)
+        out["windows"] = len(starts) * world
+    out["ok"] = out["qad_words_differing"] == 0 and out["boundaries_differing"] == 0
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -173,11 +269,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=30, help="samples per GPU = 2**log2n (default 1 GiSample)")
-    ap.add_argument("--cpu-log2n", type=int, default=24)
+    ap.add_argument("--cpu-log2n", type=int, default=26)
     ap.add_argument("--center", default="detect", choices=["detect", "given"],
                     help="detect: demod + detect_center + digitize (BASELINE configs[1]); given: fused demod+digitize, center known")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
 
     rank = env_int("RANK", 0)
@@ -197,7 +294,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = cpu_reference_arm(1 << args.cpu_log2n, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)), detect=args.center == "detect")
+        r = cpu_reference_arm(1 << args.cpu_log2n, 5, max(1, min(args.warmup, 2)), detect=args.center == "detect")
         line = dict(base)
         line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"],
                      "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -269,16 +366,17 @@ def main():
 
     def step_detect():
         if world > 1:
-            center = udist.detect_center_distributed(ctx, rank, world, sb, NOISE_MAG, "FSK", d_qad)
+            center, k = udist.demod_center_digitize_distributed(ctx, rank, world, sb, offset, n_total, NOISE_MAG, "FSK", TOL, SPS, d_qad,
+                                                                fetch=False)
             dense_of_step[0] = read_dense_ms()
             center_seen[0] = center
-            return udist.demod_digitize_distributed(ctx, rank, world, sb, offset, n_total, NOISE_MAG, "FSK", float(center), TOL, SPS,
-                                                    fetch=False, qad_source=d_qad)
-        _, center = AI.demod_detect_center(d_iq, NOISE_MAG, "FSK", out=d_qad)
+            return k
+        center, state, k = C.c_double(0.0), C.c_int(0), C.c_int64(0)
+        ctx.check(lib.urh_demod_center_digitize(ctx.handle, C.c_void_p(d_iq.ptr), _lib.DT_F32, n, NOISE_MAG, _lib.MOD_FSK, TOL, SPS, -1,
+                                                C.c_void_p(d_qad.ptr), C.byref(center), C.byref(state), C.byref(k)))
+        assert state.value == 1, "detect_center: state %d" % state.value
         dense_of_step[0] = read_dense_ms()
-        center_seen[0] = center
-        k = C.c_int64(0)
-        ctx.check(lib.urh_grab_pulse_lens(ctx.handle, C.c_void_p(d_qad.ptr), n, float(center), TOL, _lib.MOD_FSK, SPS, 1, 0.1, C.byref(k)))
+        center_seen[0] = center.value
         return k.value
 
     step_resident = step_detect if args.center == "detect" else step_given
@@ -314,6 +412,27 @@ def main():
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # ---- parity of the last timed step against the CPU oracle (outside the timed region) ----------------------------
+    parity = None
+    if not args.no_parity:
+        rows_last = np.empty((k_rows, 2), dtype=np.int64)
+        if k_rows:
+            ctx.check(lib.urh_fetch_pulses(ctx.handle, rows_last.ctypes.data_as(C.c_void_p), k_rows))
+        lens = int(rows_last[:, 1].sum())
+        if dist is not None:
+            import torch
+
+            t = torch.tensor([lens], dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            lens = int(t.item())
+        c_used = center_seen[0] if args.center == "detect" else CENTER
+        parity = parity_block(ctx, rank, world, dist, d_iq, sb.halo.get() if world > 1 else None, d_qad, rows_last, c_used, n, n_total,
+                              offset)
+        parity["sum_of_pulse_lengths_is_n_minus_tol"] = lens == n_total - TOL
+        parity["ok"] = bool(parity["ok"] and parity["sum_of_pulse_lengths_is_n_minus_tol"])
+        del rows_last
+        barrier()
 
     # ---- the other variant, for the record (not the headline): same capture, same timing rules, fewer steps ------
     other = step_given if args.center == "detect" else step_detect
@@ -436,23 +555,36 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     dense = float(np.mean(dense_ms))
     achieved = ALG_BYTES_PER_SAMPLE * n / (dense * 1e-3) / 1e9
+    kernel_key = "k_fsk_fast<F32,WRITE,STATS>" if args.center == "detect" else "k_fsk_fast<F32,DIGITIZE,WRITE>"
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(TRAFFIC_FILE))
+        ent = tj.get(args.center)
+        if ent:
+            traffic = float(ent["dram_bytes_per_sample"]) * n
+            traffic_src = "%s (%s, ncu --set full, scaled by n)" % (os.path.relpath(TRAFFIC_FILE, ROOT), ent.get("capture", ""))
+    except Exception:
+        pass
+    step_bytes = STEP_BYTES_PER_SAMPLE[args.center]
+    step_gbs = step_bytes * n * world / (ms_per_step * 1e-3) / 1e9 / world   # per GPU
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (TRAFFIC_B_PER_SAMPLE[args.center] * n) if TRAFFIC_B_PER_SAMPLE[args.center] else None, "traffic_source": TRAFFIC_SOURCE,
-                "kernel": "k_fsk_fast<F32,WRITE,STATS> (demod + tile statistics)" if args.center == "detect"
-                else "k_fsk_fast<F32,DIGITIZE,WRITE> (fused demod + classify + runs)", "kernel_ms": dense,
-                "algorithmic_bytes_per_launch": ALG_BYTES_PER_SAMPLE * n, "peak_source": peak_src,
-                "kernel_share_of_step": dense / ms_per_step}
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": kernel_key + (" (demod + tile statistics)" if args.center == "detect" else " (fused demod + classify + runs)"),
+                "kernel_ms": dense, "algorithmic_bytes_per_launch": ALG_BYTES_PER_SAMPLE * n, "peak_source": peak_src,
+                "kernel_share_of_step": dense / ms_per_step,
+                # the whole step against the same peak: SURVEY 8d's per-path byte budget / ms_per_step (per GPU)
+                "step_bytes_per_sample": step_bytes, "step_achieved": step_gbs, "step_frac": step_gbs / peak}
 
     cpu = None
     if not args.no_cpu and world == 1:
         # bounded CPU sample of the same capture (first 2^cpu_log2n samples)
         ncpu = min(n, 1 << args.cpu_log2n)
         sl = d_iq[:ncpu].get()
-        r = cpu_reference_arm(ncpu, 2, 1, iq_slice=sl)
+        r = cpu_reference_arm(ncpu, 3, 1, iq_slice=sl, detect=args.center == "detect")
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = dict(base)
-    line.update({"value": value, "ms_per_step": ms_per_step, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+    line.update({"value": value, "ms_per_step": ms_per_step, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
                  "gpu_launches": int(launches), "clocks": clocks, "pulse_rows_per_step": int(k_rows),
                  "detected_center": center_seen[0], "other_variant": other_line, "stage_ms": stages,
                  "device": info["name"], "sm_count": info["sm_count"]})

@@ -170,6 +170,25 @@ int urh_shard_candidates(urh_ctx* ctx, int carry_valid, int carry_cls, int64_t c
 int urh_shard_fire(urh_ctx* ctx, int prev_cls, int64_t* fired, int64_t* last_fired_pos);
 int urh_shard_rows(urh_ctx* ctx, int64_t n_total, uint16_t tolerance, int mod_type, uint32_t samples_per_symbol,
                    int64_t prev_fired_pos, int emit_tail, int64_t* k);
+/* One-call variants: every stage is enqueued on the context stream, the host synchronises once at the end.
+ * urh_demod_center_digitize: afp_demod (ASK/FSK) + AutoInterpretation.detect_center (AutoInterpretation.py:226-277, capture-wide)
+ *   + grab_pulse_lens (signal_functions.pyx:392-495, binary symbols) = BASELINE configs[1].  *center_state: 0 no center (None),
+ *   1 *center valid and the pulse table is ready (urh_fetch_pulses), 2 the device could not decide (a tie between histogram
+ *   peaks whose order np.argsort defines, or > 6000 bins): d_qad_out is valid, finish with the stepwise entry points.
+ * urh_shard_*: this rank's shard of a capture spread over the ranks of the context's NCCL communicator; the
+ *   exchanges (run carry, candidate class, firing position; kept counts, window partials, histogram) are NCCL calls on the
+ *   stream.  Every rank ends with the rows of its own shard. */
+int urh_demod_center_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_mag, int mod_type,
+                              uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size, float* d_qad_out,
+                              double* center, int* center_state, int64_t* k);
+int urh_shard_demod_center_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int has_halo, float noise_mag,
+                                    int mod_type, uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size,
+                                    float* d_qad_out, int64_t global_offset, int64_t n_total, double* center,
+                                    int* center_state, int64_t* k);
+int urh_shard_digitize(urh_ctx* ctx, const void* d_iq, int dtype, const float* d_qad_in, int64_t n, int has_halo,
+                       float noise_mag, int mod_type, float center, uint16_t tolerance, uint32_t samples_per_symbol,
+                       uint8_t bits_per_symbol, float center_spacing, float* d_qad_out, int64_t global_offset,
+                       int64_t n_total, int64_t* k);
 int urh_pulses_from_table(urh_ctx* ctx, const int64_t* d_pos, const int16_t* d_cls, int64_t count, int64_t n_total,
                           uint16_t tolerance, int mod_type, uint32_t samples_per_symbol, int init_cls, int64_t* k);
 /* PSK (Costas loop) over shards: speculate concurrently on every rank, then hand the loop state from rank to rank */

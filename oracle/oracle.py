@@ -444,3 +444,60 @@ def convert_iq(data, target_dtype):
         if tgt == np.uint16:
             return np.multiply(np.add(d, 1.0, dtype=np.float32), 32767, dtype=np.float32).astype(np.uint16)
     raise NotImplementedError("Conversion from {} to {} not supported", src, tgt)
+
+
+# ---- pulses -> bits (test oracle for bits.cu) ---------------------------------------------------------------------------
+def number_to_bits(n: int, length: int) -> list:
+    """util.number_to_bits (src/urh/util/util.py): MSB-first bit list of fixed length"""
+    return [int(c) for c in format(int(n), "0{}b".format(length))]
+
+
+def ppseq_to_bits(ppseq, samples_per_symbol, bits_per_symbol, write_bit_sample_pos=True, pause_threshold=8):
+    """Sequential restatement of ProtocolAnalyzer._ppseq_to_bits (src/urh/signalprocessing/ProtocolAnalyzer.py:323-414): the
+    checker for urh_ppseq_to_bits (bits.cu).  Pinned to the reference's method by tests/test_host_vs_reference.py."""
+    import array
+    positions, all_positions = array.array("L", []), []
+    bits, all_bits = array.array("B", []), []
+    pauses = array.array("L", [])
+    first, total = 0, 0
+    there_was_data = False
+    samples_per_bit = int(samples_per_symbol / bits_per_symbol)
+    if len(ppseq) > 0 and ppseq[0, 0] == -1:
+        first, total = 1, int(ppseq[0, 1])  # capture starts with a pause
+    for i in range(first, len(ppseq)):
+        kind, num_samples = int(ppseq[i, 0]), int(ppseq[i, 1])
+        num_symbols_float = num_samples / samples_per_symbol
+        num_symbols = int(num_symbols_float)
+        if num_symbols_float - num_symbols > 0.5:
+            num_symbols += 1
+        if kind == -1:
+            if num_symbols <= pause_threshold or pause_threshold == 0:
+                bits.extend([0] * (num_symbols * bits_per_symbol))
+                if write_bit_sample_pos:
+                    positions.extend([total + k * samples_per_bit for k in range(num_symbols * bits_per_symbol)])
+            elif not there_was_data:
+                bits = array.array("B", [])
+                positions = array.array("L", [])
+            else:
+                if write_bit_sample_pos:
+                    positions.append(total)
+                    positions.append(total + num_samples)
+                    all_positions.append(positions[:])
+                    positions = array.array("L", [])
+                all_bits.append(bits[:])
+                bits = array.array("B", [])
+                pauses.append(num_samples)
+                there_was_data = False
+        else:
+            bits.extend(number_to_bits(kind, bits_per_symbol) * num_symbols)
+            if not there_was_data and num_symbols > 0:
+                there_was_data = True
+            if write_bit_sample_pos:
+                positions.extend([total + k * samples_per_bit for k in range(num_symbols * bits_per_symbol)])
+        total += num_samples
+    if there_was_data:
+        all_bits.append(bits[:])
+        if write_bit_sample_pos:
+            all_positions.append(positions[:] + array.array("L", [total]))
+        pauses.append(int(ppseq[-1, 1]) if ppseq[-1, 0] == -1 else 0)
+    return all_bits, pauses, all_positions

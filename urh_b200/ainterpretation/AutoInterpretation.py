@@ -386,7 +386,7 @@ def estimate(iq_array, noise: float = None, modulation: str = None) -> dict:
     if isinstance(iq_array, np.ndarray):
         iq_array = IQArray(iq_array)
     ctx = _lib.default_context()
-    d_iq = to_device(np.ascontiguousarray(iq_array.data), ctx)  # one upload, everything below stays in HBM
+    d_iq = to_device(np.ascontiguousarray(iq_array._peek()), ctx)  # one upload, everything below stays in HBM
     d_mag = util.get_magnitudes(d_iq)
     noise = detect_noise_level(d_mag) if noise is None else noise
     message_indices = segment_messages_from_magnitudes(d_mag, noise_threshold=noise)

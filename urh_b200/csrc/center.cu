@@ -102,6 +102,7 @@ __device__ __forceinline__ void cen_block_fold(double sum, double sq, float mn, 
     __shared__ double s_sum[256], s_sq[256];
     __shared__ float s_mn[256], s_mx[256];
     __shared__ long long s_cnt[256];
+    __syncthreads();   // a block may fold twice (device-resident chain): the previous result has been read
     s_sum[threadIdx.x] = sum; s_sq[threadIdx.x] = sq; s_mn[threadIdx.x] = mn; s_mx[threadIdx.x] = mx; s_cnt[threadIdx.x] = cnt;
     __syncthreads();
     for (int off = 128; off > 0; off >>= 1) {
@@ -380,9 +381,9 @@ __device__ __forceinline__ void hist_flush(HistCache& hc, unsigned int* s_hist, 
 // Tiles strictly between win[0] and win[1] lie entirely inside the rank window: every kept sample counts, no rank
 // bookkeeping, no prefix reads.  One warp per tile, grid-stride, eight 512-byte rows in flight per warp.
 template <bool SMEM, bool FAST>
-__global__ void __launch_bounds__(256, 4) k_hist_interior(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ win,
-                                                      const float* __restrict__ g_fe, float scale, int nbins,
-                                                      unsigned long long* __restrict__ hist, int edges_in_smem) {
+__device__ __forceinline__ void hist_interior_body(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ win,
+                                                   const float* __restrict__ g_fe, float scale, int nbins,
+                                                   unsigned long long* __restrict__ hist, int edges_in_smem) {
     extern __shared__ unsigned int s_dyn[];
     unsigned int* s_hist = s_dyn;                               // [nbins] when SMEM
     float* s_fe = (float*)(s_dyn + (SMEM ? nbins : 0));         // [nbins + 3] when edges_in_smem
@@ -438,11 +439,18 @@ __global__ void __launch_bounds__(256, 4) k_hist_interior(const float* __restric
     }
 }
 
+template <bool SMEM, bool FAST>
+__global__ void __launch_bounds__(256, 4) k_hist_interior(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ win,
+                                                      const float* __restrict__ g_fe, float scale, int nbins,
+                                                      unsigned long long* __restrict__ hist, int edges_in_smem) {
+    hist_interior_body<SMEM, FAST>(x, n, win, g_fe, scale, nbins, hist, edges_in_smem);
+}
+
 // the window's first and last tile (win[0], win[1]; one block each): rank-exact, straight to the global histogram
-__global__ void __launch_bounds__(256) k_hist_window_ends(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ prefix,
-                                                         const int64_t* __restrict__ win, int64_t r0, int64_t r1,
-                                                         const float* __restrict__ g_fe, float scale, int nbins,
-                                                         unsigned long long* __restrict__ hist) {
+__device__ __forceinline__ void hist_window_ends_body(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ prefix,
+                                                      const int64_t* __restrict__ win, int64_t r0, int64_t r1,
+                                                      const float* __restrict__ g_fe, float scale, int nbins,
+                                                      unsigned long long* __restrict__ hist) {
     __shared__ int s_pre[256];
     const int64_t t = win[blockIdx.x];
     if (t < 0 || (blockIdx.x == 1 && t == win[0])) return;
@@ -457,6 +465,13 @@ __global__ void __launch_bounds__(256) k_hist_window_ends(const float* __restric
         if (k >= 0 && rank >= r0 && rank < r1) atomicAdd(&hist[k], 1ull);
         rank += kept ? 1 : 0;
     }
+}
+
+__global__ void __launch_bounds__(256) k_hist_window_ends(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ prefix,
+                                                         const int64_t* __restrict__ win, int64_t r0, int64_t r1,
+                                                         const float* __restrict__ g_fe, float scale, int nbins,
+                                                         unsigned long long* __restrict__ hist) {
+    hist_window_ends_body(x, n, prefix, win, r0, r1, g_fe, scale, nbins, hist);
 }
 
 // Counts for edges hmin + k*hstep, k = 0..nbins (np.arange) over the samples of LOCAL rank [r0, r1); needs the tile
@@ -510,4 +525,389 @@ extern "C" int urh_center_histogram(urh_ctx* ctx, const float* d_x, int64_t n, i
         URH_CHECK(tiles_from_array(ctx, d_x, n, &total));
     }
     return urh_center_histogram_tiles(ctx, d_x, n, r0, r1, hmin, hstep, nbins, h_hist);
+}
+
+// =============================================================================================================================
+// Device-resident chain: demod tile table -> window -> bin edges -> histogram -> peak pick -> center, with no host
+// round trip in between (the host reads {center, state} once, together with the digitizer's row count).  The decisions
+// the stepwise API leaves to numpy on the host are restated here (AutoInterpretation.py:226-277):
+//   * rank window  int(0.05 * kept) .. int(0.95 * kept)  (double product, truncation), capped by max_size
+//   * np.arange(min, max + var, var): length ceil((stop - start) / step); elements start, start + step, then start + k * delta
+//     with delta = (start + step) - start
+//   * peak pick: a peak exceeds every neighbour within max(2, int(0.05 * nbins) + 1) bins; the two most populated peaks; center =
+//     mean of their left edges.  np.argsort's order among EQUAL counts is implementation-defined, so a tie that would decide
+//     which peak is taken hands the decision back to the host path (state 2), as do more than CEN_MAX_BINS bins.
+// Sharded captures: the kept counts, the window partials and the histogram are exchanged with NCCL on the context stream.
+// =============================================================================================================================
+#include "tilescan.cuh"
+
+#define CEN_MAX_BINS 6000
+
+struct __align__(16) CenterPlan {
+    long long total, offset;   // kept samples of the capture / of the preceding shards
+    long long r0, r1;          // global rank window
+    long long lr0, lr1;        // this shard's part of it (local ranks)
+    long long win[4];          // window tiles (k_find_window_tiles layout)
+    CenStats local;            // this shard's window partial
+    double hmin, edge1, delta;
+    long long nbins;
+    double center;
+    float centerf;             // the digitizer's threshold
+    float scale;
+    int fast;
+    int state;                 // 0: no center; 1: center found / histogram to be built; 2: host path must decide
+    unsigned int ticket;
+    int pad;
+};
+
+struct ScanKept {
+    const UrhTileStats* ts;
+    int64_t* prefix;
+    __device__ __forceinline__ int64_t load(int64_t t) const { return ts[t].cnt; }
+    __device__ __forceinline__ void post(int64_t t, const int64_t& excl, const int64_t&) const { prefix[t] = excl; }
+};
+struct CenAddI64 {
+    __device__ __forceinline__ int64_t operator()(int64_t a, int64_t b) const { return a + b; }
+};
+
+// counts: this shard's kept total (world == 1) or the gathered totals of all ranks
+__global__ void k_center_ranks(const int64_t* __restrict__ counts, int rank, int world, int64_t max_size, CenterPlan* __restrict__ plan) {
+    long long total = 0, offset = 0;
+    for (int q = 0; q < world; q++) {
+        if (q < rank) offset += counts[q];
+        total += counts[q];
+    }
+    const long long kept = counts[rank];
+    long long r0 = (long long)(0.05 * (double)total), r1 = (long long)(0.95 * (double)total);
+    if (max_size >= 0 && r1 - r0 > max_size) r1 = r0 + max_size;
+    plan->total = total; plan->offset = offset; plan->r0 = r0; plan->r1 = r1;
+    long long a = r0 - offset, b = r1 - offset;
+    a = a < 0 ? 0 : (a > kept ? kept : a);
+    b = b < 0 ? 0 : (b > kept ? kept : b);
+    plan->lr0 = a; plan->lr1 = b;
+    plan->ticket = 0u;
+    plan->state = 1;
+}
+
+// last tile t with prefix[t] <= r (prefix has ntiles + 1 entries, prefix[ntiles] = kept): the tile holding local rank r
+__device__ __forceinline__ int64_t cen_tile_of_rank(const int64_t* __restrict__ prefix, int64_t ntiles, int64_t r) {
+    int64_t lo = 0, hi = ntiles;   // invariant: prefix[lo] <= r, prefix[hi] > r  (prefix[0] = 0 <= r < kept = prefix[ntiles])
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (prefix[mid] <= r) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// window tiles + {count, min, max, sum, sumsq} of this shard's window: interior tiles from the table (grid-stride), the two
+// cut tiles rank-exactly (blocks 0 and 1), folded by the last block to finish.  partial: gridDim.x + 2 entries.
+__global__ void __launch_bounds__(256) k_center_window(const float* __restrict__ x, int64_t n, const UrhTileStats* __restrict__ ts,
+                                                      const int64_t* __restrict__ prefix, int64_t ntiles, CenterPlan* __restrict__ plan,
+                                                      CenStats* __restrict__ partial) {
+    __shared__ long long s_win[4];
+    __shared__ int s_pre[256];
+    __shared__ bool s_last;
+    const long long r0 = plan->lr0, r1 = plan->lr1;
+    if (threadIdx.x == 0) {
+        long long w0 = -1, w1 = -1, w2 = -1, w3 = -1;
+        if (r1 > r0) {
+            w0 = cen_tile_of_rank(prefix, ntiles, r0);
+            w1 = cen_tile_of_rank(prefix, ntiles, r1 - 1);
+            const bool cov0 = prefix[w0] >= r0 && prefix[w0 + 1] <= r1;
+            const bool cov1 = prefix[w1] >= r0 && prefix[w1 + 1] <= r1;
+            w2 = cov0 ? -1 : w0;
+            w3 = (cov1 || w1 == w0) ? -1 : w1;
+        }
+        s_win[0] = w0; s_win[1] = w1; s_win[2] = w2; s_win[3] = w3;
+        if (blockIdx.x == 0) { plan->win[0] = w0; plan->win[1] = w1; plan->win[2] = w2; plan->win[3] = w3; }
+    }
+    __syncthreads();
+    double sum = 0.0, sq = 0.0;
+    float mn = INFINITY, mx = -INFINITY;
+    long long cnt = 0;
+    if (s_win[0] >= 0) {
+        for (int64_t t = s_win[0] + (int64_t)blockIdx.x * 256 + threadIdx.x; t <= s_win[1]; t += (int64_t)gridDim.x * 256) {
+            const int64_t a = prefix[t], b = prefix[t + 1];
+            if (b > a && a >= r0 && b <= r1) {
+                const UrhTileStats v = ts[t];
+                sum += v.sum; sq += v.sumsq; mn = fminf(mn, v.mn); mx = fmaxf(mx, v.mx); cnt += v.cnt;
+            }
+        }
+    }
+    cen_block_fold(sum, sq, mn, mx, cnt, partial + blockIdx.x);
+    if (blockIdx.x < 2) {
+        const int64_t t = s_win[2 + blockIdx.x];
+        sum = 0.0; sq = 0.0; mn = INFINITY; mx = -INFINITY; cnt = 0;
+        if (t >= 0) {
+            float v[CEN_PER];
+            int64_t rank = cen_tile_ranks(x, n, t, prefix[t], v, s_pre);
+#pragma unroll
+            for (int j = 0; j < CEN_PER; j++) {
+                if (v[j] > -4.0f) {
+                    if (rank >= r0 && rank < r1) {
+                        sum += (double)v[j];
+                        sq += (double)v[j] * (double)v[j];
+                        mn = fminf(mn, v[j]);
+                        mx = fmaxf(mx, v[j]);
+                        cnt++;
+                    }
+                    rank++;
+                }
+            }
+        }
+        cen_block_fold(sum, sq, mn, mx, cnt, partial + gridDim.x + blockIdx.x);
+    }
+    // the last block to arrive folds every partial in index order (deterministic)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&plan->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    sum = 0.0; sq = 0.0; mn = INFINITY; mx = -INFINITY; cnt = 0;
+    for (int64_t t = threadIdx.x; t < (int64_t)gridDim.x + 2; t += 256) {
+        CenStats p;   // written by other blocks: read through L2
+        {
+            const int4* src = (const int4*)(partial + t);
+            int4 w0 = __ldcg(src), w1 = __ldcg(src + 1);
+            memcpy(&p, &w0, 16);
+            memcpy((char*)&p + 16, &w1, 16);
+        }
+        sum += p.sum; sq += p.sumsq; mn = fminf(mn, p.mn); mx = fmaxf(mx, p.mx); cnt += p.cnt;
+    }
+    cen_block_fold(sum, sq, mn, mx, cnt, &plan->local);
+}
+
+// Bin edges and the launch parameters of the histogram from the (rank-ordered) window partials of all shards.
+// parts: world entries (world == 1: &plan->local).  fe: CEN_MAX_BINS + 3 floats; hist: CEN_MAX_BINS counters (zeroed here).
+__global__ void __launch_bounds__(256) k_center_plan(const CenStats* __restrict__ parts, int world, CenterPlan* __restrict__ plan,
+                                                    float* __restrict__ fe, unsigned long long* __restrict__ hist) {
+    __shared__ int s_state;
+    __shared__ long long s_nbins;
+    __shared__ double s_hmin, s_edge1, s_delta;
+    if (threadIdx.x == 0) {
+        double cnt = 0.0, sum = 0.0, sq = 0.0;
+        float mn = INFINITY, mx = -INFINITY;
+        for (int q = 0; q < world; q++) {   // rank order: every rank (and every world size's replay) folds identically
+            cnt += (double)parts[q].cnt;
+            mn = fminf(mn, parts[q].mn);
+            mx = fmaxf(mx, parts[q].mx);
+            sum = __dadd_rn(sum, parts[q].sum);
+            sq = __dadd_rn(sq, parts[q].sumsq);
+        }
+        int state = 0;
+        long long nbins = 0;
+        double hmin = 0.0, edge1 = 0.0, delta = 0.0;
+        if (plan->r1 > plan->r0 && cnt > 0.0) {
+            const double mean = __ddiv_rn(sum, cnt);
+            double ss = __dsub_rn(sq, __dmul_rn(__dmul_rn(cnt, mean), mean));
+            if (ss < 0.0) ss = 0.0;
+            const double var = __ddiv_rn(ss, cnt);
+            const double hstep = (double)__double2float_rn(var);   // np.var of a float32 array is a float32
+            hmin = (double)mn;
+            const double stop = __dadd_rn((double)mx, hstep);
+            if (hstep != 0.0) {
+                const double val = __ddiv_rn(__dsub_rn(stop, hmin), hstep);
+                if (val == val && fabs(val) < 9.0e18) {
+                    const long long len = (long long)ceil(val);
+                    if (len >= 2) {
+                        nbins = len - 1;
+                        edge1 = __dadd_rn(hmin, hstep);
+                        delta = __dsub_rn(edge1, hmin);
+                        state = (nbins <= CEN_MAX_BINS && delta > 0.0) ? 1 : 2;
+                    }
+                }
+            }
+        }
+        plan->hmin = hmin; plan->edge1 = edge1; plan->delta = delta; plan->nbins = nbins;
+        plan->state = state;
+        plan->center = 0.0; plan->centerf = 0.0f;
+        if (state == 1) {
+            plan->scale = (float)(1.0 / delta);
+            const double edge_abs = fmax(fabs(hmin), fabs(hmin + (double)nbins * delta));
+            plan->fast = (edge_abs / delta < 1048576.0) ? 1 : 0;
+        }
+        s_state = state; s_nbins = nbins; s_hmin = hmin; s_edge1 = edge1; s_delta = delta;
+    }
+    __syncthreads();
+    if (s_state != 1) return;
+    const long long nbins = s_nbins;
+    for (long long k = threadIdx.x; k <= nbins; k += 256) {
+        const double e = (k == 0) ? s_hmin : (k == 1 ? s_edge1 : __dadd_rn(s_hmin, __dmul_rn((double)k, s_delta)));
+        fe[k] = __double2float_ru(e);
+        if (k == nbins) {
+            fe[nbins + 1] = __double2float_rd(e);
+            fe[nbins + 2] = fmaxf(__double2float_ru(s_hmin), nextafterf(-4.0f, 0.0f));
+        }
+        if (k < nbins) hist[k] = 0ull;
+    }
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(256, 4) k_hist_interior_dev(const float* __restrict__ x, int64_t n, const CenterPlan* __restrict__ plan,
+                                                          const float* __restrict__ g_fe, unsigned long long* __restrict__ hist) {
+    if (plan->state != 1 || (plan->fast != 0) != FAST) return;
+    hist_interior_body<true, FAST>(x, n, (const int64_t*)plan->win, g_fe, plan->scale, (int)plan->nbins, hist, 1);
+}
+__global__ void __launch_bounds__(256) k_hist_window_ends_dev(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ prefix,
+                                                             const CenterPlan* __restrict__ plan, const float* __restrict__ g_fe,
+                                                             unsigned long long* __restrict__ hist) {
+    if (plan->state != 1) return;
+    hist_window_ends_body(x, n, prefix, (const int64_t*)plan->win, plan->lr0, plan->lr1, g_fe, plan->scale, (int)plan->nbins, hist);
+}
+
+// peak pick (one block).  y = hist[0..nbins)
+__global__ void __launch_bounds__(256) k_center_pick(const unsigned long long* __restrict__ y, CenterPlan* __restrict__ plan) {
+    __shared__ unsigned long long s_best[256];
+    __shared__ int s_idx[256];
+    __shared__ int s_cnt[256];
+    if (plan->state != 1) return;
+    const int nbins = (int)plan->nbins;
+    int window = (int)(0.05 * (double)nbins) + 1;
+    if (window < 2) window = 2;
+    // pass 1: best peak; pass 2: best peak among the others.  Ties that matter -> state 2.
+    unsigned long long top_val[2] = {0ull, 0ull};
+    int top_idx[2] = {-1, -1};
+    int found = 0;
+    bool undecided = false;
+    for (int pass = 0; pass < 2 && !undecided; pass++) {
+        unsigned long long best = 0ull;
+        int bi = -1, ties = 0;
+        for (int i = threadIdx.x; i < nbins; i += 256) {
+            if (pass == 1 && i == top_idx[0]) continue;
+            const unsigned long long v = y[i];
+            if (v == 0ull || v < best) continue;
+            bool peak = true;
+            for (int d = 1; d < window && peak; d++) {
+                const unsigned long long a = (i + d < nbins) ? y[i + d] : 0ull;
+                const unsigned long long b = (i - d >= 0) ? y[i - d] : 0ull;
+                peak = v > a && v > b;
+            }
+            if (!peak) continue;
+            if (v > best) { best = v; bi = i; ties = 1; }
+            else ties++;
+        }
+        s_best[threadIdx.x] = best; s_idx[threadIdx.x] = bi; s_cnt[threadIdx.x] = ties;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long b = 0ull;
+            int idx = -1, t = 0;
+            for (int j = 0; j < 256; j++) {
+                if (s_idx[j] < 0) continue;
+                if (s_best[j] > b) { b = s_best[j]; idx = s_idx[j]; t = s_cnt[j]; }
+                else if (s_best[j] == b) t += s_cnt[j];
+            }
+            s_best[0] = b; s_idx[0] = idx; s_cnt[0] = t;
+        }
+        __syncthreads();
+        const unsigned long long b = s_best[0];
+        const int idx = s_idx[0], t = s_cnt[0];
+        __syncthreads();
+        if (idx < 0) break;
+        if (pass == 0) {
+            top_val[0] = b; top_idx[0] = idx; found = 1;
+            if (t == 2) {
+                // exactly two peaks share the top count: both are taken, in either order (the mean is symmetric).  Find the other.
+                int other = -1;
+                for (int i = threadIdx.x; i < nbins; i += 256) {
+                    if (i == idx || y[i] != b) continue;
+                    bool peak = true;
+                    for (int d = 1; d < window && peak; d++) {
+                        const unsigned long long a = (i + d < nbins) ? y[i + d] : 0ull;
+                        const unsigned long long c = (i - d >= 0) ? y[i - d] : 0ull;
+                        peak = b > a && b > c;
+                    }
+                    if (peak) other = i;
+                }
+                s_idx[threadIdx.x] = other;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int o = -1;
+                    for (int j = 0; j < 256; j++) if (s_idx[j] >= 0) o = s_idx[j];
+                    s_idx[0] = o;
+                }
+                __syncthreads();
+                top_idx[1] = s_idx[0]; top_val[1] = b; found = 2;
+                __syncthreads();
+                break;
+            }
+            if (t > 2) undecided = true;
+        } else {
+            if (t > 1) undecided = true;
+            else { top_val[1] = b; top_idx[1] = idx; found = 2; }
+        }
+    }
+    if (threadIdx.x != 0) return;
+    if (undecided) { plan->state = 2; return; }
+    if (found == 0) { plan->state = 0; return; }
+    auto edge = [&](int k) { return (k == 0) ? plan->hmin : (k == 1 ? plan->edge1 : __dadd_rn(plan->hmin, __dmul_rn((double)k, plan->delta))); };
+    double c;
+    if (found == 1) c = edge(top_idx[0]);
+    else c = __ddiv_rn(__dadd_rn(edge(top_idx[0]), edge(top_idx[1])), 2.0);
+    plan->center = c;
+    plan->centerf = __double2float_rn(c);
+    plan->state = 1;
+    (void)top_val;
+}
+
+extern "C" int urh_nccl_allgather(urh_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
+extern "C" int urh_nccl_allreduce_i64(urh_ctx* ctx, int64_t* d_buf, int64_t count, int op);
+
+// The chain.  ts = the demodulator's tile table of d_qad (arena); *d_plan_out stays valid until the next arena reset.
+// Enqueues everything on the context stream; no synchronisation.  world > 1: the context's NCCL communicator.
+int urh_center_chain(urh_ctx* ctx, const float* d_qad, int64_t n, const UrhTileStats* ts, int64_t max_size, int rank, int world,
+                     CenterPlan** d_plan_out) {
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    int64_t* prefix;
+    CenterPlan* plan;
+    CenStats* partial;
+    float* fe;
+    unsigned long long* hist;
+    int64_t* d_counts;
+    CenStats* d_parts;
+    const int nb = ctx->sm_count * 2;
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles + 1, &prefix));
+    URH_CHECK(urh_arena(ctx, 1, &plan));
+    URH_CHECK(urh_arena(ctx, (size_t)nb + 2, &partial));
+    URH_CHECK(urh_arena(ctx, (size_t)CEN_MAX_BINS + 3, &fe));
+    URH_CHECK(urh_arena(ctx, (size_t)CEN_MAX_BINS, &hist));
+    URH_CHECK(urh_arena(ctx, (size_t)world, &d_counts));
+    URH_CHECK(urh_arena(ctx, (size_t)world, &d_parts));
+    ScanKept fk;
+    fk.ts = ts; fk.prefix = prefix;
+    URH_CHECK((urhts::scan<int64_t, CenAddI64, ScanKept>(ctx, ntiles, (int64_t)0, CenAddI64(), fk, prefix + ntiles)));
+    const int64_t* counts = prefix + ntiles;
+    if (world > 1) {
+        URH_CHECK(urh_nccl_allgather(ctx, prefix + ntiles, d_counts, sizeof(int64_t)));
+        counts = d_counts;
+    }
+    URH_LAUNCH(ctx, k_center_ranks, 1, 1, 0, counts, rank, world, max_size, plan);
+    URH_LAUNCH(ctx, k_center_window, nb, 256, 0, d_qad, n, ts, (const int64_t*)prefix, ntiles, plan, partial);
+    const CenStats* parts = &plan->local;
+    if (world > 1) {
+        URH_CHECK(urh_nccl_allgather(ctx, &plan->local, d_parts, sizeof(CenStats)));
+        parts = d_parts;
+    }
+    URH_LAUNCH(ctx, k_center_plan, 1, 256, 0, parts, world, plan, fe, hist);
+    const size_t dyn = (size_t)CEN_MAX_BINS * 4 + (size_t)(CEN_MAX_BINS + 3) * 4;   // histogram + edge table, 48 KB
+    const unsigned gs = (unsigned)min(urh_div_up(ntiles, 8), (int64_t)ctx->sm_count * 8);
+    URH_LAUNCH(ctx, (k_hist_interior_dev<true>), gs, 256, dyn, d_qad, n, (const CenterPlan*)plan, (const float*)fe, hist);
+    URH_LAUNCH(ctx, (k_hist_interior_dev<false>), gs, 256, dyn, d_qad, n, (const CenterPlan*)plan, (const float*)fe, hist);
+    URH_LAUNCH(ctx, k_hist_window_ends_dev, 2, 256, 0, d_qad, n, (const int64_t*)prefix, (const CenterPlan*)plan, (const float*)fe, hist);
+    if (world > 1) URH_CHECK(urh_nccl_allreduce_i64(ctx, (int64_t*)hist, CEN_MAX_BINS, 0));
+    URH_LAUNCH(ctx, k_center_pick, 1, 256, 0, (const unsigned long long*)hist, plan);
+    ctx->center_prefix = prefix;
+    ctx->center_ts = ts;
+    ctx->center_n = n;
+    ctx->center_x = d_qad;
+    *d_plan_out = plan;
+    return URH_OK;
+}
+
+// {center (double), state} of a plan -> 16 bytes at dst (device or pinned host), on the stream
+int urh_center_plan_result(urh_ctx* ctx, const CenterPlan* plan, const float** d_centerf, const double** d_center, const int** d_state) {
+    if (d_centerf) *d_centerf = &plan->centerf;
+    if (d_center) *d_center = &plan->center;
+    if (d_state) *d_state = &plan->state;
+    return URH_OK;
 }

@@ -77,6 +77,15 @@ struct urh_ctx {
     void* p2p_hout;
     int p2p_rank, p2p_world;
     unsigned long long p2p_seq;
+    // tilescan.cuh workspace (look-back scans over tile tables)
+    void* ts_mem;
+    int64_t ts_cap_blocks;
+    unsigned long long ts_issued;
+    uint32_t ts_epoch;
+    // finish.cu / center chain: small device-resident result block and its pinned mirror
+    void* step_dev;
+    // digitizer exchange state of a sharded capture (finish.cu)
+    void* shard_fin;
 };
 
 #define URH_CUDA(ctx, call)                                                                         \

@@ -1,5 +1,6 @@
 // Context, memory, timing and the scratch arena of liburh_b200.
 #include "common.cuh"
+#include "tilescan.cuh"
 
 extern "C" int urh_device_count(void) {
     int n = 0;
@@ -93,6 +94,9 @@ extern "C" void urh_ctx_destroy(urh_ctx* ctx) {
     if (ctx->pulses) cudaFree(ctx->pulses);
     if (ctx->shard_state) free(ctx->shard_state);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
+    if (ctx->ts_mem) cudaFree(ctx->ts_mem);
+    if (ctx->step_dev) cudaFree(ctx->step_dev);
+    if (ctx->shard_fin) free(ctx->shard_fin);
     for (int i = 0; i < 2; i++)
         if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
     cudaEventDestroy(ctx->ev_start);
@@ -276,6 +280,38 @@ int urh_ensure_pulses(urh_ctx* ctx, size_t rows) {
     size_t cap = rows + rows / 4;
     URH_CUDA(ctx, cudaMalloc((void**)&ctx->pulses, cap * 2 * sizeof(int64_t)));
     ctx->pulses_cap_rows = cap;
+    return URH_OK;
+}
+
+// Workspace of the look-back scans (tilescan.cuh): [counter 256 B][status 4 B x cap][agg SLOT x cap][pre SLOT x cap].
+// Zeroed once; launches are told apart by their epoch and by the counter value their first block will draw.
+int urhts::prepare(urh_ctx* ctx, int64_t nblocks, urhts::Ws* out) {
+    if (nblocks > ctx->ts_cap_blocks) {
+        if (ctx->ts_mem) {
+            URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            URH_CUDA(ctx, cudaFree(ctx->ts_mem));
+            ctx->ts_mem = nullptr;
+            ctx->ts_cap_blocks = 0;
+        }
+        int64_t cap = nblocks * 2 > 8192 ? nblocks * 2 : 8192;
+        cap = (cap + 63) & ~(int64_t)63;
+        const size_t bytes = 256 + (size_t)cap * (4 + 2 * urhts::SLOT);
+        URH_CUDA(ctx, cudaMalloc(&ctx->ts_mem, bytes));
+        URH_CUDA(ctx, cudaMemsetAsync(ctx->ts_mem, 0, bytes, ctx->stream));
+        ctx->ts_cap_blocks = cap;
+        ctx->ts_issued = 0;
+        ctx->ts_epoch = 0;
+    }
+    char* base = (char*)ctx->ts_mem;
+    out->counter = (unsigned long long*)base;
+    out->status = (uint32_t*)(base + 256);
+    out->agg = base + 256 + (size_t)ctx->ts_cap_blocks * 4;
+    out->pre = out->agg + (size_t)ctx->ts_cap_blocks * urhts::SLOT;
+    out->base = ctx->ts_issued;
+    ctx->ts_issued += (unsigned long long)nblocks;
+    ctx->ts_epoch = (ctx->ts_epoch + 1) & 0x3fffffffu;
+    if (ctx->ts_epoch == 0) ctx->ts_epoch = 1;   // 0 is the zero-initialised "never written" state
+    out->epoch = ctx->ts_epoch;
     return URH_OK;
 }
 

@@ -6,19 +6,19 @@
 
 // Classifier sources for the stand-alone digitizer / segmenter: float32 samples already in memory.
 struct SrcQad {  // grab_pulse_lens on a demodulated array
-    template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C) { return urh_classify((float)s, C); }
+    template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C, float) { return urh_classify((float)s, C); }
 };
 struct SrcQad2 {  // the same for a binary digitizer (order 2): no threshold loop, no branches
-    template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C) {
-        const int c = ((float)s <= C.thr[0]) ? 0 : 1;
+    template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C, float thr0) {
+        const int c = ((float)s <= thr0) ? 0 : 1;
         return ((float)s == C.noise_value) ? -1 : c;
     }
 };
 struct SrcAbove {  // segment_messages_from_magnitudes: class 1 = above noise (auto_interpretation.pyx:79)
-    template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C) { return (s > (T)C.thr[0]) ? 1 : 0; }
+    template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify&, float thr0) { return (s > (T)thr0) ? 1 : 0; }
 };
 struct SrcCenter {  // get_plateau_lengths: -1/1 around center (auto_interpretation.pyx:183,197) as 0/1
-    template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C) { return (s <= (T)C.thr[0]) ? 0 : 1; }
+    template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify&, float thr0) { return (s <= (T)thr0) ? 0 : 1; }
 };
 
 template <typename T> struct UrhVec2;
@@ -29,7 +29,10 @@ template <typename SRC, typename T>
 __global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32)
 k_dense_f32(const T* __restrict__ x, int64_t n, int vec_in, const __grid_constant__ UrhClassify cls, int tol,
             UrhTileSummary* __restrict__ tiles, uint32_t* __restrict__ staging, int stage_cap,
-            int16_t* __restrict__ init_cls, int cls_of_zero) {
+            int16_t* __restrict__ init_cls, int cls_of_zero, const float* __restrict__ d_thr0 = nullptr) {
+    // d_thr0: the (binary) threshold lives in device memory (center detected on the device); then cls_of_zero is derived here
+    const float thr0 = d_thr0 ? *d_thr0 : cls.thr[0];
+    if (d_thr0) cls_of_zero = (0.0f <= thr0) ? 0 : 1;
     const int lane = threadIdx.x & 31;
     const int64_t tile = (int64_t)blockIdx.x * URH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int64_t tile_start = tile * URH_TILE;
@@ -54,7 +57,7 @@ k_dense_f32(const T* __restrict__ x, int64_t n, int vec_in, const __grid_constan
             }
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                rt.feed(it + j, SRC::template cls<T>(cur[j].x, cls), SRC::template cls<T>(cur[j].y, cls), true, true, lane);
+                rt.feed(it + j, SRC::template cls<T>(cur[j].x, cls, thr0), SRC::template cls<T>(cur[j].y, cls, thr0), true, true, lane);
 #pragma unroll
             for (int j = 0; j < 4; j++) cur[j] = nxt[j];
         }
@@ -84,8 +87,8 @@ k_dense_f32(const T* __restrict__ x, int64_t n, int vec_in, const __grid_constan
             }
         }
         if (pa == 0 && init_cls) *init_cls = (int16_t)(((float)a0 == cls.noise_value) ? -1 : cls_of_zero);
-        rt.feed(it, SRC::template cls<T>(a0, cls), SRC::template cls<T>(a1, cls), pa < n, pa + 1 < n, lane);
-        if (has_b) rt.feed(it + 1, SRC::template cls<T>(b0, cls), SRC::template cls<T>(b1, cls), pb < n, pb + 1 < n, lane);
+        rt.feed(it, SRC::template cls<T>(a0, cls, thr0), SRC::template cls<T>(a1, cls, thr0), pa < n, pa + 1 < n, lane);
+        if (has_b) rt.feed(it + 1, SRC::template cls<T>(b0, cls, thr0), SRC::template cls<T>(b1, cls, thr0), pb < n, pb + 1 < n, lane);
     }
     rt.finish(tile_len, tiles + tile, lane);
 }

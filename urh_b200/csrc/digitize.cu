@@ -12,6 +12,7 @@
 #include "dense_f32.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 // =====================================================================================================
 // Dense kernels
@@ -287,11 +288,19 @@ extern "C" int urh_afp_demod_tiles(urh_ctx* ctx, const void* d_iq, int dtype, in
 }
 
 // Shared tail of the two digitizer entry points: tile table + staging -> merged (state, length) rows.
+int urh_finish_local(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t sps, const UrhTileSummary* tiles, const uint32_t* staging,
+                     int stage_cap, const int16_t* d_init, int64_t* k);   // finish.cu
+int urh_finish_shard(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t sps, const UrhTileSummary* tiles, const uint32_t* staging,
+                     int stage_cap, const int16_t* d_init, int64_t global_offset, int64_t n_total, int64_t* k);   // finish.cu
+
 static int digitize_finish(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t sps, UrhTileSummary* tiles,
                            uint32_t* staging, int stage_cap, int16_t* d_init, int64_t* k) {
-    UrhCandidates cand;
-    URH_CHECK(urh_collect_candidates(ctx, n, tol, tiles, staging, stage_cap, &cand));
-    return urh_pulses_from_candidates(ctx, n, tol, is_ask, sps, cand, d_init, k);
+    if (getenv("URH_B200_OLD_FINISH")) {   // the candidate-table formulation (kept for the segmenter; A/B switch for measurements)
+        UrhCandidates cand;
+        URH_CHECK(urh_collect_candidates(ctx, n, tol, tiles, staging, stage_cap, &cand));
+        return urh_pulses_from_candidates(ctx, n, tol, is_ask, sps, cand, d_init, k);
+    }
+    return urh_finish_local(ctx, n, tol, is_ask, sps, tiles, staging, stage_cap, d_init, k);
 }
 
 static int stage_cap_for(int tol) { return URH_TILE / (tol + 1) + 2; }
@@ -457,6 +466,145 @@ extern "C" int urh_shard_dense_qad(urh_ctx* ctx, const float* d_qad, int64_t n, 
     URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     h_summary[3] = init16;
     return URH_OK;
+}
+
+// ---- one-call paths: every stage enqueued on the context stream, ONE synchronisation at the end -----------------------------
+struct CenterPlan;
+int urh_center_chain(urh_ctx* ctx, const float* d_qad, int64_t n, const UrhTileStats* ts, int64_t max_size, int rank, int world,
+                     CenterPlan** d_plan_out);   // center.cu
+int urh_center_plan_result(urh_ctx* ctx, const CenterPlan* plan, const float** d_centerf, const double** d_center, const int** d_state);
+
+// Sharded demod + digitize for a KNOWN center: dense pass over this rank's shard, then the tile-level finish with
+// its three 16-byte exchanges on the stream (finish.cu).  d_qad_in != NULL: the shard is already demodulated, digitize from it.
+// Every rank ends with the rows of its own shard (urh_fetch_pulses).
+extern "C" int urh_shard_digitize(urh_ctx* ctx, const void* d_iq, int dtype, const float* d_qad_in, int64_t n, int has_halo,
+                                  float noise_mag, int mod_type, float center, uint16_t tolerance, uint32_t samples_per_symbol,
+                                  uint8_t bits_per_symbol, float center_spacing, float* d_qad_out, int64_t global_offset,
+                                  int64_t n_total, int64_t* k) {
+    if (!k) return URH_ERR_INVALID;
+    *k = 0;
+    ctx->pulses_k = 0;
+    if (n <= 0) URH_FAIL(ctx, URH_ERR_INVALID, "empty shard");
+    if (mod_type != URH_MOD_ASK && mod_type != URH_MOD_FSK) URH_FAIL(ctx, URH_ERR_INVALID, "sharded path: ASK / FSK only");
+    if (!d_qad_in && urh_iq_bytes(dtype) == 0) URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
+    if (!ctx->nccl_comm) URH_FAIL(ctx, URH_ERR_INVALID, "NCCL communicator not initialised (urh_nccl_init)");
+    urh_arena_reset(ctx);
+    UrhClassify cls;
+    URH_CHECK(fill_classify(ctx, &cls, mod_type, center, bits_per_symbol, center_spacing));
+    const int tol = tolerance;
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    const int cap = stage_cap_for(tol);
+    UrhTileSummary* tiles;
+    uint32_t* staging;
+    int16_t* d_init;
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles, &tiles));
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles * cap, &staging));
+    URH_CHECK(urh_arena(ctx, 8, &d_init));
+    URH_CUDA(ctx, cudaMemsetAsync(d_init, 0, 16, ctx->stream));
+    const int c0 = host_classify(0.0f, cls);
+    if (d_qad_in) {
+        const int vec_in = (((uintptr_t)d_qad_in % 8) == 0) ? 1 : 0;
+        const unsigned grid = (unsigned)urh_div_up(ntiles, URH_WARPS_PER_BLOCK);
+        URH_PROF_BEGIN(ctx);
+        if (cls.order == 2)
+            URH_LAUNCH(ctx, (k_dense_f32<SrcQad2, float>), grid, URH_WARPS_PER_BLOCK * 32, 0, d_qad_in, n, vec_in, cls, tol, tiles, staging, cap,
+                       d_init, c0, (const float*)nullptr);
+        else
+            URH_LAUNCH(ctx, (k_dense_f32<SrcQad, float>), grid, URH_WARPS_PER_BLOCK * 32, 0, d_qad_in, n, vec_in, cls, tol, tiles, staging, cap,
+                       d_init, c0, (const float*)nullptr);
+        URH_PROF_END(ctx);
+    } else {
+        const UrhDemodParams dp = make_demod_params(noise_mag, mod_type, dtype);
+        if (mod_type == URH_MOD_ASK)
+            URH_CHECK((launch_dense_iq_m<URH_MOD_ASK, true>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, tol, tiles, staging, cap, d_init, c0, has_halo)));
+        else
+            URH_CHECK((launch_dense_iq_m<URH_MOD_FSK, true>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, tol, tiles, staging, cap, d_init, c0, has_halo)));
+    }
+    return urh_finish_shard(ctx, n, tol, mod_type == URH_MOD_ASK, samples_per_symbol, tiles, staging, cap, d_init, global_offset, n_total, k);
+}
+
+// demod (ASK / FSK) + capture-wide detect_center + digitize (binary symbols) in one call (BASELINE configs[1]).
+// sharded != 0: this rank's shard of a capture spread over the context's NCCL communicator (has_halo as urh_shard_dense).
+// *center_state: 0 = detect_center finds no center (None; *k = 0), 1 = *center is valid, 2 = the device could not decide
+// (a tie between histogram peaks whose order numpy's argsort defines, or more than 6000 bins): d_qad_out is valid, the
+// caller finishes through the stepwise entry points (urh_center_window_stats / urh_center_histogram_tiles / urh_grab_pulse_lens).
+static int demod_center_digitize_impl(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int has_halo, float noise_mag, int mod_type,
+                                      uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size, float* d_qad_out, bool sharded,
+                                      int64_t global_offset, int64_t n_total, double* center, int* center_state, int64_t* k) {
+    if (!k || !center || !center_state) return URH_ERR_INVALID;
+    *k = 0;
+    *center = 0.0;
+    *center_state = 0;
+    ctx->pulses_k = 0;
+    if (n <= 2 || (mod_type != URH_MOD_ASK && mod_type != URH_MOD_FSK) || !d_qad_out)
+        URH_FAIL(ctx, URH_ERR_INVALID, "demod_center_digitize: ASK/FSK, n > 2 and a qad buffer are required");
+    if (urh_iq_bytes(dtype) == 0) URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
+    if (sharded && !ctx->nccl_comm) URH_FAIL(ctx, URH_ERR_INVALID, "NCCL communicator not initialised (urh_nccl_init)");
+    urh_arena_reset(ctx);
+    const UrhDemodParams dp = make_demod_params(noise_mag, mod_type, dtype);
+    UrhClassify cls;
+    memset(&cls, 0, sizeof(cls));
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    UrhTileStats* ts;
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles, &ts));
+    if (mod_type == URH_MOD_ASK)
+        URH_CHECK((launch_dense_iq_m<URH_MOD_ASK, false>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, 0, nullptr, nullptr, 0, nullptr, 0, has_halo, ts)));
+    else
+        URH_CHECK((launch_dense_iq_m<URH_MOD_FSK, false>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, 0, nullptr, nullptr, 0, nullptr, 0, has_halo, ts)));
+    CenterPlan* plan = nullptr;
+    URH_CHECK(urh_center_chain(ctx, d_qad_out, n, ts, max_size, sharded ? ctx->nccl_rank : 0, sharded ? ctx->nccl_world : 1, &plan));
+    const float* d_centerf;
+    const double* d_center;
+    const int* d_state;
+    urh_center_plan_result(ctx, plan, &d_centerf, &d_center, &d_state);
+    // digitizer pass over qad, threshold read from device memory
+    cls.noise_value = urh_noise_value(mod_type);
+    cls.order = 2;
+    const int tol = tolerance;
+    const int cap = stage_cap_for(tol);
+    UrhTileSummary* tiles;
+    uint32_t* staging;
+    int16_t* d_init;
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles, &tiles));
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles * cap, &staging));
+    URH_CHECK(urh_arena(ctx, 8, &d_init));
+    URH_CUDA(ctx, cudaMemsetAsync(d_init, 0, 16, ctx->stream));
+    const int vec_in = (((uintptr_t)d_qad_out % 8) == 0) ? 1 : 0;
+    URH_LAUNCH(ctx, (k_dense_f32<SrcQad2, float>), (unsigned)urh_div_up(ntiles, URH_WARPS_PER_BLOCK), URH_WARPS_PER_BLOCK * 32, 0,
+               (const float*)d_qad_out, n, vec_in, cls, tol, tiles, staging, cap, d_init, 0, d_centerf);
+    URH_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 40, d_center, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 41, d_state, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    int64_t rows = 0;
+    if (sharded)
+        URH_CHECK(urh_finish_shard(ctx, n, tol, mod_type == URH_MOD_ASK, samples_per_symbol, tiles, staging, cap, d_init, global_offset, n_total, &rows));
+    else
+        URH_CHECK(urh_finish_local(ctx, n, tol, mod_type == URH_MOD_ASK, samples_per_symbol, tiles, staging, cap, d_init, &rows));
+    // the finish synchronised the stream: the two scalars have landed
+    memcpy(center, ctx->h_mail + 40, sizeof(double));
+    int st = 0;
+    memcpy(&st, ctx->h_mail + 41, sizeof(int));
+    *center_state = st;
+    if (st != 1) {
+        ctx->pulses_k = 0;
+        rows = 0;
+    }
+    *k = rows;
+    return URH_OK;
+}
+
+extern "C" int urh_demod_center_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_mag, int mod_type,
+                                         uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size, float* d_qad_out,
+                                         double* center, int* center_state, int64_t* k) {
+    return demod_center_digitize_impl(ctx, d_iq, dtype, n, 0, noise_mag, mod_type, tolerance, samples_per_symbol, max_size, d_qad_out, false,
+                                      0, n, center, center_state, k);
+}
+
+extern "C" int urh_shard_demod_center_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int has_halo, float noise_mag,
+                                               int mod_type, uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size,
+                                               float* d_qad_out, int64_t global_offset, int64_t n_total, double* center,
+                                               int* center_state, int64_t* k) {
+    return demod_center_digitize_impl(ctx, d_iq, dtype, n, has_halo, noise_mag, mod_type, tolerance, samples_per_symbol, max_size, d_qad_out,
+                                      true, global_offset, n_total, center, center_state, k);
 }
 
 struct UrhShardState {

@@ -2,30 +2,7 @@
 #include "sparse.cuh"
 #include "scan.cuh"
 
-// ---- run stitching across tiles ---------------------------------------------------------------------
-struct __align__(16) RunCarry {
-    int64_t len;    // length of the run that ends at the end of the span
-    int32_t cls;    // its class
-    int32_t flags;  // bit0: the whole span is one run; bit1: empty span (identity)
-};
-struct RunCarryOp {
-    __device__ __forceinline__ RunCarry operator()(const RunCarry& a, const RunCarry& b) const {
-        if (b.flags & 2) return a;
-        if (a.flags & 2) return b;
-        RunCarry r;
-        if ((b.flags & 1) && b.cls == a.cls) {
-            r.len = a.len + b.len;
-            r.cls = a.cls;
-            r.flags = a.flags & 1;
-        } else {
-            r.len = b.len;
-            r.cls = b.cls;
-            r.flags = 0;
-        }
-        return r;
-    }
-};
-
+// ---- run stitching across tiles (RunCarry / RunCarryOp: sparse.cuh) -------------------------------------
 __global__ void k_tile_elems(const UrhTileSummary* __restrict__ tiles, int64_t ntiles, int64_t n, RunCarry* __restrict__ e) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;

@@ -3,6 +3,31 @@
 #pragma once
 #include "dense.cuh"
 
+// The run that ends at the end of a span of tiles, and the associative operator that concatenates two spans.
+struct __align__(16) RunCarry {
+    int64_t len;    // length of the run that ends at the end of the span
+    int32_t cls;    // its class
+    int32_t flags;  // bit0: the whole span is one run; bit1: empty span (identity)
+};
+struct RunCarryOp {
+    __device__ __forceinline__ RunCarry operator()(const RunCarry& a, const RunCarry& b) const {
+        if (b.flags & 2) return a;
+        if (a.flags & 2) return b;
+        RunCarry r;
+        if ((b.flags & 1) && b.cls == a.cls) {
+            r.len = a.len + b.len;
+            r.cls = a.cls;
+            r.flags = a.flags & 1;
+        } else {
+            r.len = b.len;
+            r.cls = b.cls;
+            r.flags = 0;
+        }
+        return r;
+    }
+};
+
+
 struct UrhCandidates {
     int64_t count;   // number of candidates (host copy)
     int64_t* pos;    // device: absolute sample index run_start + tolerance

@@ -124,13 +124,37 @@ def demod_digitize(samples, noise_mag: float, mod_type: str, center: float, tole
 
 
 def demod_center_digitize(samples, noise_mag: float, mod_type: str, tolerance: int, samples_per_symbol: int,
-                          bits_per_symbol: int = 1, center_spacing: float = 0.1, max_size=None, return_qad: bool = False):
-    """afp_demod -> detect_center -> grab_pulse_lens for a capture whose center is not known yet (ASK/FSK): two passes
-    over the IQ-rate data instead of the reference's five (demod+statistics, histogram of qad, then digitize from qad).
+                          bits_per_symbol: int = 1, center_spacing: float = 0.1, max_size=None, return_qad: bool = False,
+                          stepwise: bool = False, out=None):
+    """afp_demod -> detect_center -> grab_pulse_lens for a capture whose center is not known yet (ASK/FSK): three passes
+    over sample-rate data instead of the reference's five (demod + tile statistics, histogram of qad, digitize from qad).
+    Binary symbols run as ONE library call (urh_demod_center_digitize): bin edges, histogram, peak pick and the pulse table
+    are chained on the device and the host synchronises once.  ``stepwise`` (or a tie the device must not break, or
+    bits_per_symbol > 1) takes the call-by-call path with the peak pick in numpy.
     Returns (center, int64[k,2]) or (center, rows, qad) with return_qad.  center None -> no pulses (empty table)."""
     from urh_b200.ainterpretation.AutoInterpretation import demod_detect_center
     on_device = isinstance(samples, DeviceArray)
-    qad, center = demod_detect_center(samples, noise_mag, mod_type, max_size)
+    code = _lib.demod_mod_code(mod_type)
+    one_call = not stepwise and bits_per_symbol == 1 and code in (_lib.MOD_ASK, _lib.MOD_FSK) and len(samples) > 2
+    qad = out
+    if one_call:
+        samples = _check_iq(samples)
+        ctx = samples.ctx if on_device else _lib.default_context()
+        n = len(samples)
+        d_iq = samples if on_device else to_device(samples, ctx)
+        if qad is None:
+            qad = DeviceArray(ctx, (n,), np.float32)
+        center, state, k = C.c_double(0.0), C.c_int(0), C.c_int64(0)
+        ctx.check(ctx.lib.urh_demod_center_digitize(ctx.handle, C.c_void_p(d_iq.ptr), _lib.dtype_code(d_iq.dtype), n, float(noise_mag),
+                                                    code, int(tolerance), int(samples_per_symbol), -1 if max_size is None else int(max_size),
+                                                    C.c_void_p(qad.ptr), C.byref(center), C.byref(state), C.byref(k)))
+        if state.value != 2:
+            c = float(center.value) if state.value == 1 else None
+            rows = _fetch_pulses(ctx, k.value) if c is not None else np.zeros((0, 2), dtype=np.int64)
+            if return_qad:
+                return c, rows, (qad if on_device else qad.get())
+            return c, rows
+    qad, center = demod_detect_center(samples, noise_mag, mod_type, max_size, out=qad)
     if center is None:
         rows = np.zeros((0, 2), dtype=np.int64)
     else:

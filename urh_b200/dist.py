@@ -224,6 +224,32 @@ def previous_nonempty(values, counts, rank, default):
 def demod_digitize_distributed(ctx, rank, world, sb: ShardBuffer, global_offset, n_total, noise_mag, mod_type, center, tolerance,
                                samples_per_symbol, bits_per_symbol=1, center_spacing=0.1, d_qad=None, fetch=True, qad_source=None):
     """Sharded FSK/ASK demod + digitize with a DISTRIBUTED finish: no gather, every rank ends with the rows of its own
+    shard (``merge_shard_rows`` joins them).  One library call per rank (urh_shard_digitize): the dense pass, then the
+    tile-level finish whose three 16-byte exchanges (run carry / class of the last candidate / position of the last firing)
+    are NCCL all-gathers enqueued on the context stream — the host waits once, for the row count.
+    ``qad_source``: the shard is already demodulated (float32 DeviceArray) -> digitize from it instead of the IQ samples."""
+    if os.environ.get("URH_B200_DIST_STEPWISE"):
+        return demod_digitize_distributed_stepwise(ctx, rank, world, sb, global_offset, n_total, noise_mag, mod_type, center, tolerance,
+                                                   samples_per_symbol, bits_per_symbol, center_spacing, d_qad, fetch, qad_source)
+    lib = ctx.lib
+    code = _lib.demod_mod_code(mod_type)
+    k = C.c_int64(0)
+    ctx.check(lib.urh_shard_digitize(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype),
+                                     C.c_void_p(qad_source.ptr if qad_source is not None else 0), sb.n, int(rank > 0), float(noise_mag), code,
+                                     float(center), int(tolerance), int(samples_per_symbol), int(bits_per_symbol), float(center_spacing),
+                                     C.c_void_p(d_qad.ptr if d_qad is not None else 0), int(global_offset), int(n_total), C.byref(k)))
+    if not fetch:
+        return int(k.value)
+    rows = np.empty((k.value, 2), dtype=np.int64)
+    if k.value:
+        ctx.check(lib.urh_fetch_pulses(ctx.handle, rows.ctypes.data_as(C.c_void_p), k.value))
+    return rows
+
+
+def demod_digitize_distributed_stepwise(ctx, rank, world, sb: ShardBuffer, global_offset, n_total, noise_mag, mod_type, center, tolerance,
+                               samples_per_symbol, bits_per_symbol=1, center_spacing=0.1, d_qad=None, fetch=True, qad_source=None):
+    """Call-by-call variant (host folds between the stages; kept as the reference for the one-call path).
+    Sharded FSK/ASK demod + digitize with a DISTRIBUTED finish: no gather, every rank ends with the rows of its own
     shard (``merge_shard_rows`` joins them).  Three NCCL all-gathers of a few int64 per rank are the whole exchange:
       (last_cls, last_len, whole, init_cls)  ->  run carry into the shard;
       (candidate count, class of the last candidate)  ->  fire decision of the shard's first candidate;
@@ -325,8 +351,28 @@ def detect_center_distributed(ctx, rank, world, sb: ShardBuffer, noise_mag, mod_
 
 def demod_center_digitize_distributed(ctx, rank, world, sb: ShardBuffer, global_offset, n_total, noise_mag, mod_type, tolerance,
                                       samples_per_symbol, d_qad, bits_per_symbol=1, center_spacing=0.1, max_size=None, fetch=True):
-    """BASELINE configs[1]/[4] on N GPUs: demod + capture-wide detect_center + digitize of ONE sharded capture.
+    """BASELINE configs[1]/[4] on N GPUs: demod + capture-wide detect_center + digitize of ONE sharded capture, one library
+    call per rank (urh_shard_demod_center_digitize).  Exchanges, all NCCL on the context stream with device buffers: kept
+    counts (8 B), window partials (32 B), the histogram all-reduce, then the digitizer's three 16-byte all-gathers.
     The digitizer pass reads the shard's qad (4 B/sample) once the center is known.  -> (center, rows or count)."""
+    lib = ctx.lib
+    code = _lib.demod_mod_code(mod_type)
+    if bits_per_symbol == 1 and not os.environ.get("URH_B200_DIST_STEPWISE"):
+        center, state, k = C.c_double(0.0), C.c_int(0), C.c_int64(0)
+        ctx.check(lib.urh_shard_demod_center_digitize(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, int(rank > 0),
+                                                      float(noise_mag), code, int(tolerance), int(samples_per_symbol),
+                                                      -1 if max_size is None else int(max_size), C.c_void_p(d_qad.ptr), int(global_offset),
+                                                      int(n_total), C.byref(center), C.byref(state), C.byref(k)))
+        if state.value == 0:
+            return None, (np.zeros((0, 2), dtype=np.int64) if fetch else 0)
+        if state.value == 1:
+            if not fetch:
+                return float(center.value), int(k.value)
+            rows = np.empty((k.value, 2), dtype=np.int64)
+            if k.value:
+                ctx.check(lib.urh_fetch_pulses(ctx.handle, rows.ctypes.data_as(C.c_void_p), k.value))
+            return float(center.value), rows
+        # state 2: a tie the device must not break (every rank sees the same histogram, so every rank lands here together)
     center = detect_center_distributed(ctx, rank, world, sb, noise_mag, mod_type, d_qad, max_size)
     if center is None:
         return None, (np.zeros((0, 2), dtype=np.int64) if fetch else 0)

@@ -2,7 +2,7 @@
 modulates a message list into a shared ring buffer.  Same interface; the child (``spawn``, which CUDA needs and URH
 already forces) modulates runs of messages that share a modulator as one GPU batch instead of one call per message."""
 import time
-from multiprocessing import Value, get_context
+from multiprocessing import get_context
 
 from .. import settings
 from ..util.RingBuffer import RingBuffer
@@ -18,9 +18,9 @@ class ContinuousModulator(object):
         self.modulators = modulators
         self.num_repeats = num_repeats  # -1 or 0 = infinite
         self.ring_buffer = RingBuffer(int(settings.CONTINUOUS_BUFFER_SIZE_MB * 1e6) // 8, dtype=Modulator.get_dtype())
-        self.current_message_index = Value("L", 0)
-        self.abort = Value("i", 0)
         self._mp = get_context("spawn")
+        self.current_message_index = self._mp.Value("L", 0)
+        self.abort = self._mp.Value("i", 0)
         self.process = self._mp.Process(target=self.modulate_continuously, args=(self.num_repeats,), daemon=True)
 
     @property

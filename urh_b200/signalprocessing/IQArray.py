@@ -17,7 +17,7 @@ _INT_TYPES = (np.uint8, np.int8, np.uint16, np.int16)
 
 
 class IQArray(object):
-    def __init__(self, data: np.ndarray, dtype=None, n=None, skip_conversion=False):
+    def __init__(self, data: np.ndarray, dtype=None, n=None, skip_conversion=False, _owned=False):
         if data is None:
             self.__data = np.zeros((n, 2), dtype, order="C")
         elif skip_conversion:
@@ -26,10 +26,28 @@ class IQArray(object):
             self.__data = self.convert_array_to_iq(data)
         assert self.__data.dtype not in (np.complex64, np.complex128)
         self._device = None
+        # the caller may keep (and later write) the array it passed in unless we made our own copy
+        self._aliased = data is not None and not _owned   # _owned: the caller hands the array over and keeps no reference
 
     # -- numpy-like access -------------------------------------------------------------------------------------
+    # The HBM copy (`device()`) must never go stale.  Every accessor that hands out a WRITABLE numpy view of the samples
+    # (`data`, `real`, `imag`, `iq[...]`, `convert_to` of the same dtype — the reference lets callers write through them,
+    # e.g. ``iq.data[a:b] = 0``) marks the object as aliased: the view may be written at any later time, so from then on
+    # `device()` uploads afresh on every call instead of trusting a cached copy.  Readers inside the package use
+    # `_peek()`, a read-only view, and keep the cache.
+    def _alias(self):
+        self._device = None
+        self._aliased = True
+
     def __getitem__(self, item):
+        self._alias()
         return self.__data[item]
+
+    def _peek(self, item=None):
+        view = self.__data.view() if item is None else self.__data[item]
+        if isinstance(view, np.ndarray):
+            view.flags.writeable = False
+        return view
 
     def __setitem__(self, key, value):
         self._device = None
@@ -50,7 +68,7 @@ class IQArray(object):
         return len(self.__data)
 
     def __eq__(self, other):
-        return np.array_equal(self.data, other.data)
+        return np.array_equal(self._peek(), other._peek() if isinstance(other, IQArray) else other.data)
 
     @property
     def num_samples(self):
@@ -66,10 +84,12 @@ class IQArray(object):
 
     @property
     def data(self):
+        self._alias()
         return self.__data
 
     @property
     def real(self):
+        self._alias()
         return self.__data[:, 0]
 
     @real.setter
@@ -79,6 +99,7 @@ class IQArray(object):
 
     @property
     def imag(self):
+        self._alias()
         return self.__data[:, 1]
 
     @imag.setter
@@ -95,9 +116,18 @@ class IQArray(object):
         """the capture as a DeviceArray (uploaded once, invalidated by in-place edits through this object)"""
         from ..device import to_device
 
+        if self._aliased:
+            return to_device(np.ascontiguousarray(self.__data))   # a writable view is out there: never cache
         if self._device is None or len(self._device) != len(self.__data):
             self._device = to_device(np.ascontiguousarray(self.__data))
         return self._device
+
+    def own(self):
+        """take a private copy of the samples: no outside view can reach them any more, so `device()` may cache again"""
+        self.__data = np.array(self.__data, order="C")
+        self._device = None
+        self._aliased = False
+        return self
 
     @property
     def magnitudes(self):
@@ -114,7 +144,7 @@ class IQArray(object):
         return self.__data.tobytes()
 
     def subarray(self, start=None, stop=None, step=None):
-        return IQArray(np.ascontiguousarray(self[start:stop:step]))
+        return IQArray(np.array(self._peek(slice(start, stop, step)), order="C"), _owned=True)
 
     def insert_subarray(self, pos, subarray: np.ndarray):
         self._device = None
@@ -136,6 +166,7 @@ class IQArray(object):
         the dtype already matches."""
         tgt = np.dtype(target_dtype)
         if tgt == self.__data.dtype:
+            self._alias()
             return self.__data
         if tgt not in [np.dtype(t) for t in _INT_TYPES + (np.float32,)]:
             raise ValueError("Data type {} not supported".format(target_dtype))
@@ -178,11 +209,11 @@ class IQArray(object):
     @staticmethod
     def from_file(filename: str):
         dt = IQArray._dtype_for_filename(filename)
-        arr = IQArray(data=np.fromfile(filename, dtype=dt))
+        arr = IQArray(data=np.fromfile(filename, dtype=dt), _owned=True)
         if dt == np.uint8:
-            return IQArray(arr.convert_to(np.int8))      # unsigned captures are handled as signed
+            return IQArray(arr.convert_to(np.int8), _owned=True)      # unsigned captures are handled as signed
         if dt == np.uint16:
-            return IQArray(arr.convert_to(np.int16))
+            return IQArray(arr.convert_to(np.int16), _owned=True)
         return arr
 
     @staticmethod
@@ -207,7 +238,7 @@ class IQArray(object):
 
     @staticmethod
     def concatenate(*args):
-        return IQArray(data=np.concatenate([a.data if isinstance(a, IQArray) else a for a in args[0]]))
+        return IQArray(data=np.concatenate([a._peek() if isinstance(a, IQArray) else a for a in args[0]]), _owned=True)
 
     def save_compressed(self, filename):
         with tarfile.open(filename, "w:bz2") as tar_write:

@@ -129,7 +129,7 @@ class Modulator(object):
         result = signal_functions.modulate_c(
             data, self.samples_per_symbol, self.modulation_type, parameters, self.bits_per_symbol, a, self.carrier_freq_hz,
             self.carrier_phase_deg * (np.pi / 180), self.sample_rate, pause, start, dtype, self.gauss_bt, self.gauss_filter_width)
-        return IQArray(result)
+        return IQArray(result, _owned=True)
 
     def modulate_batch(self, messages, pauses, start=0, dtype=None) -> list:
         """All messages in one GPU batch (what modulate_messages / ContinuousModulator loop over in the reference);
@@ -142,7 +142,7 @@ class Modulator(object):
             [p[0] for p in prepared], self.samples_per_symbol, self.modulation_type, parameters, self.bits_per_symbol, a,
             self.carrier_freq_hz, self.carrier_phase_deg * (np.pi / 180), self.sample_rate, pauses, start, dt, self.gauss_bt,
             self.gauss_filter_width)
-        return [IQArray(r) for r in res]
+        return [IQArray(r, _owned=True) for r in res]
 
     def get_default_parameters(self) -> array.array:
         if self.is_amplitude_based:

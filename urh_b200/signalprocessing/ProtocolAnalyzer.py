@@ -1,17 +1,12 @@
 """Pulses -> bits: the caller side of the digitizer (reference: ProtocolAnalyzer.get_protocol_from_signal
 ProtocolAnalyzer.py:227-285 and _ppseq_to_bits :323-414).  Only what is needed to turn the pulse table into the bit
 strings the reference's demodulation tests assert on; the protocol container / labels / decodings are out of scope.
-The Python loop over the k pulse rows is row f-1 of the scope table ("next": move to the device)."""
+The row loop runs on the GPU (bits.cu); its sequential CPU restatement lives in oracle/oracle.py (ppseq_to_bits), test-only."""
 import array
 
 import numpy as np
 
 from ..cythonext import signal_functions
-
-
-def number_to_bits(n: int, length: int) -> list:
-    """util.number_to_bits (src/urh/util/util.py): MSB-first bit list of fixed length"""
-    return [int(c) for c in format(int(n), "0{}b".format(length))]
 
 
 class LiteMessage(object):
@@ -94,51 +89,3 @@ class ProtocolAnalyzer(object):
                     continue
                 bit_sample_pos[i].extend([bit_sample_pos[i][-1] + (k + 1) * samples_per_symbol for k in range(missing - 1)])
                 bit_sample_pos[i].append(bit_sample_pos[i][-1] + pauses[i])
-
-    @staticmethod
-    def _ppseq_to_bits(ppseq, samples_per_symbol, bits_per_symbol, write_bit_sample_pos=True, pause_threshold=8):
-        positions, all_positions = array.array("L", []), []
-        bits, all_bits = array.array("B", []), []
-        pauses = array.array("L", [])
-        first, total = 0, 0
-        there_was_data = False
-        samples_per_bit = int(samples_per_symbol / bits_per_symbol)
-        if len(ppseq) > 0 and ppseq[0, 0] == -1:
-            first, total = 1, int(ppseq[0, 1])  # capture starts with a pause
-        for i in range(first, len(ppseq)):
-            kind, num_samples = int(ppseq[i, 0]), int(ppseq[i, 1])
-            num_symbols_float = num_samples / samples_per_symbol
-            num_symbols = int(num_symbols_float)
-            if num_symbols_float - num_symbols > 0.5:
-                num_symbols += 1
-            if kind == -1:
-                if num_symbols <= pause_threshold or pause_threshold == 0:
-                    bits.extend([0] * (num_symbols * bits_per_symbol))
-                    if write_bit_sample_pos:
-                        positions.extend([total + k * samples_per_bit for k in range(num_symbols * bits_per_symbol)])
-                elif not there_was_data:
-                    bits = array.array("B", [])
-                    positions = array.array("L", [])
-                else:
-                    if write_bit_sample_pos:
-                        positions.append(total)
-                        positions.append(total + num_samples)
-                        all_positions.append(positions[:])
-                        positions = array.array("L", [])
-                    all_bits.append(bits[:])
-                    bits = array.array("B", [])
-                    pauses.append(num_samples)
-                    there_was_data = False
-            else:
-                bits.extend(number_to_bits(kind, bits_per_symbol) * num_symbols)
-                if not there_was_data and num_symbols > 0:
-                    there_was_data = True
-                if write_bit_sample_pos:
-                    positions.extend([total + k * samples_per_bit for k in range(num_symbols * bits_per_symbol)])
-            total += num_samples
-        if there_was_data:
-            all_bits.append(bits[:])
-            if write_bit_sample_pos:
-                all_positions.append(positions[:] + array.array("L", [total]))
-            pauses.append(int(ppseq[-1, 1]) if ppseq[-1, 0] == -1 else 0)
-        return all_bits, pauses, all_positions

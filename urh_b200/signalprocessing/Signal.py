@@ -315,7 +315,7 @@ class Signal(object):
     def create_new(self, start=0, end=0, new_data=None, new_timestamp=0):
         new_signal = Signal("", "New " + self.name)
         if new_data is None:
-            new_signal.iq_array = IQArray(self.iq_array[start:end])
+            new_signal.iq_array = IQArray(np.array(self.iq_array._peek(slice(start, end)), order="C"), _owned=True)
             new_signal.timestamp = self.timestamp + (start / self.sample_rate)
         else:
             new_signal.iq_array = IQArray(new_data)
@@ -420,7 +420,7 @@ class Signal(object):
         self.__invalidate_after_edit()
 
     def crop_to_range(self, start: int, end: int):
-        self.iq_array = IQArray(self.iq_array[start:end])
+        self.iq_array = IQArray(np.array(self.iq_array._peek(slice(start, end)), order="C"), _owned=True)
         self._qad = self._qad[start:end] if self._qad is not None else None
         self._qad_dev = None
         self.__invalidate_after_edit()

@@ -1,6 +1,6 @@
 """Shared-memory ring buffer of IQ samples between the continuous modulator process and its consumer
 (reference: src/urh/util/RingBuffer.py:7-140).  Host plumbing around the modulator; same interface."""
-from multiprocessing import Array, Value
+from multiprocessing import get_context
 
 import numpy as np
 
@@ -11,10 +11,13 @@ class RingBuffer(object):
     def __init__(self, size: int, dtype=np.float32):
         self.dtype = dtype
         self.size = size
-        self.__data = Array(_TYPECODES[dtype], 2 * size)
-        self.__left = Value("L", 0)
-        self.__right = Value("L", 0)
-        self.__length = Value("L", 0)
+        # shared objects from the SPAWN context: the producer is a spawned child (CUDA cannot be forked, and URH itself
+        # forces the spawn start method); spawn-context locks are also fine under fork
+        mp = get_context("spawn")
+        self.__data = mp.Array(_TYPECODES[dtype], 2 * size)
+        self.__left = mp.Value("L", 0)
+        self.__right = mp.Value("L", 0)
+        self.__length = mp.Value("L", 0)
 
     def __len__(self):
         return self.__length.value
