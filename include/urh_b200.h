@@ -111,6 +111,9 @@ int urh_center_histogram(urh_ctx* ctx, const float* d_x, int64_t n, int64_t r0, 
 int urh_afp_demod_tiles(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_mag, int mod_type, float* d_qad_out,
                         int halo, int64_t* h_kept);
 int urh_center_window_stats(urh_ctx* ctx, const float* d_qad, int64_t n, int64_t r0, int64_t r1, double* h_out5);
+/* {np.mean, np.var} of the same window as numpy computes them for a float32 array — float32 pairwise sums replayed bit for bit
+ * (AutoInterpretation.py:240: the histogram's bin width); urh_center_stats uses it unless URH_B200_CENTER_DOUBLE is set. */
+int urh_center_window_var(urh_ctx* ctx, const float* d_qad, int64_t n, int64_t r0, int64_t r1, double* h_out2);
 int urh_center_histogram_tiles(urh_ctx* ctx, const float* d_qad, int64_t n, int64_t r0, int64_t r1, double hmin, double hstep,
                                int64_t nbins, int64_t* h_hist);
 /* replaces auto_interpretation.segment_messages_from_magnitudes (auto_interpretation.pyx:55-111) */
@@ -196,6 +199,13 @@ int urh_costas_halo_samples(void);
 int urh_costas_shard_speculate(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int first_shard, float noise_mag,
                                int loop_order, float bandwidth, float* d_out);
 int urh_costas_shard_resolve(urh_ctx* ctx, const float* h_state_in, float* h_state_out);
+/* Sharded PSK without the rank-to-rank hand-over: after urh_costas_shard_speculate every later shard hops over its
+ * super-chunks under each hypothesis "the shard starts in candidate h's start state" (what a locked loop of the preceding shard
+ * ends in, bit for bit); h_out[h] = {start.freq, start.phase, end.freq, end.phase}, *count hypotheses (1 on the first shard).
+ * The ranks exchange these few floats, each picks the hypothesis whose start state equals the preceding shard's end state
+ * and calls urh_costas_shard_adopt; without a match the serial urh_costas_shard_resolve remains (exact either way). */
+int urh_costas_shard_hypotheses(urh_ctx* ctx, float* h_out, int* count);
+int urh_costas_shard_adopt(urh_ctx* ctx, int h, float* h_state_out);
 /* Signal.estimate_frequency (Signal.py:578-601): arg-max bin of fft(x[0:P]), P = 2^floor(log2 n) (complex64 on the device) */
 int urh_fft_argmax(urh_ctx* ctx, const float* d_x, int64_t n, int64_t* h_index, int64_t* h_P);
 /* replaces the arithmetic of IQArray.convert_to (IQArray.py:127-200): capture formats cs8/cu8/cs16/cu16/float32 into each

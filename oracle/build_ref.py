@@ -89,7 +89,48 @@ def build(force: bool = False) -> bool:
     return built()
 
 
+PYREF = os.path.join(OUT, "pyref")
+# the reference's own tests that exercise the hot path without a Qt event loop
+REF_TESTS = ["__init__.py", "utils_testing.py", "test_util.py", "test_demodulations.py", "test_modulator.py", "test_iq_array.py",
+             "test_protocol_analyzer.py", "test_ringbuffer.py", "test_continuous_modulator.py", "auto_interpretation"]
+
+
+def stage_python_layer(force: bool = False) -> bool:
+    """Stage the reference's unmodified Python layer (src/urh/**/*.py), the hot-path test files and tests/data into
+    oracle/_ref/pyref/ so that they exist on the GPU box, where /root/reference does not.  Build output like the .so
+    files: git-ignored, never part of the repository.  Used by oracle/run_reference_tests.py (drop-in proof) and by
+    bench.py's reference arm (the reference's own detect_center)."""
+    marker = os.path.join(PYREF, ".staged")
+    if not ref_available():
+        return os.path.isfile(marker)
+    if os.path.isfile(marker) and not force:
+        return True
+    shutil.rmtree(PYREF, ignore_errors=True)
+    src = os.path.join(REF, "src", "urh")
+    for root, dirs, files in os.walk(src):
+        dirs[:] = [d for d in dirs if d not in ("__pycache__", "build")]
+        rel = os.path.relpath(root, src)
+        for f in files:
+            if f.endswith((".py", ".txt", ".json", ".xml", ".fuzz", ".ini")) and not f.endswith((".pyx", ".pxd")):
+                dst = os.path.join(PYREF, "src", "urh", rel, f)
+                os.makedirs(os.path.dirname(dst), exist_ok=True)
+                shutil.copy2(os.path.join(root, f), dst)
+    tsrc = os.path.join(REF, "tests")
+    for root, dirs, files in os.walk(tsrc):   # every test module (imports between them); only REF_TESTS are run
+        dirs[:] = [d for d in dirs if d not in ("__pycache__", "data")]
+        rel = os.path.relpath(root, tsrc)
+        for f in files:
+            if f.endswith(".py"):
+                dst = os.path.join(PYREF, "tests", rel, f)
+                os.makedirs(os.path.dirname(dst), exist_ok=True)
+                shutil.copy2(os.path.join(root, f), dst)
+    shutil.copytree(os.path.join(tsrc, "data"), os.path.join(PYREF, "tests", "data"), ignore=shutil.ignore_patterns("__pycache__"))
+    open(marker, "w").write("staged from %s\n" % REF)
+    return True
+
+
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
     print("oracle/_ref built:", ok)
+    print("reference python layer staged:", stage_python_layer(force="--force" in sys.argv))
     sys.exit(0 if ok or not ref_available() else 1)

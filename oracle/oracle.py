@@ -501,3 +501,41 @@ def ppseq_to_bits(ppseq, samples_per_symbol, bits_per_symbol, write_bit_sample_p
             all_positions.append(positions[:] + array.array("L", [total]))
         pauses.append(int(ppseq[-1, 1]) if ppseq[-1, 0] == -1 else 0)
     return all_bits, pauses, all_positions
+
+
+# ---- numpy's float32 pairwise summation, restated (checker for pairwise.cu; pinned to numpy by tests/test_pairwise_model.py) ------
+def np_pairwise_sum_f32(a):
+    """numpy/_core/src/umath/loops_utils.h.src FLOAT_pairwise_sum on a contiguous float32 array (pure Python: small inputs)"""
+    f32 = np.float32
+    n = len(a)
+    if n < 8:
+        r = f32(0.0)
+        for x in a:
+            r = f32(r + x)
+        return r
+    if n <= 128:
+        r = [a[k] for k in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for k in range(8):
+                r[k] = f32(r[k] + a[i + k])
+            i += 8
+        res = f32(f32(f32(r[0] + r[1]) + f32(r[2] + r[3])) + f32(f32(r[4] + r[5]) + f32(r[6] + r[7])))
+        while i < n:
+            res = f32(res + a[i])
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return f32(np_pairwise_sum_f32(a[:n2]) + np_pairwise_sum_f32(a[n2:]))
+
+
+def np_var_f32(a):
+    """np.var of a float32 array as numpy/_core/_methods.py _var computes it: (mean, var), both float32"""
+    f32 = np.float32
+    a = np.ascontiguousarray(a, dtype=f32)
+    n = len(a)
+    mean = f32(np.float64(f32(0.0) + np_pairwise_sum_f32(a)) / np.float64(n))
+    x = (a - mean).astype(f32)
+    x = (x * x).astype(f32)
+    return mean, f32(np.float64(f32(0.0) + np_pairwise_sum_f32(x)) / np.float64(n))

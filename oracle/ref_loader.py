@@ -18,6 +18,8 @@ import types
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("URH_REFERENCE", "/root/reference")
 REF_OUT = os.path.join(HERE, "_ref")
+if not os.path.isdir(os.path.join(REF, "src", "urh")) and os.path.isdir(os.path.join(REF_OUT, "pyref", "src", "urh")):
+    REF = os.path.join(REF_OUT, "pyref")   # the staged copy (oracle/build_ref.py: stage_python_layer) on the GPU box
 
 
 def kernels_available() -> bool:
@@ -178,10 +180,11 @@ def load_kernels():
 
 
 def load_python_layer():
-    """Reference Python DSP objects (container only; never on the GPU box)."""
+    """Reference Python DSP objects: from /root/reference in the build container, from the staged copy oracle/_ref/pyref
+    on the GPU box."""
     load_kernels()
     if not os.path.isdir(os.path.join(REF, "src", "urh")):
-        raise ImportError("/root/reference not present")
+        raise ImportError("reference python layer not present (neither /root/reference nor oracle/_ref/pyref)")
     ns = types.SimpleNamespace()
     from urh.signalprocessing.Signal import Signal
     from urh.signalprocessing.IQArray import IQArray

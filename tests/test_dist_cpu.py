@@ -191,3 +191,20 @@ def test_distributed_center_protocol_gloo(tmp_path):
     port = 29450 + os.getpid() % 200
     mp.spawn(_center_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert open(tmp_path / "ok_center").read() == "1"
+
+
+def test_resolve_psk_chain():
+    """host half of the sharded Costas loop: each shard adopts the hypothesis whose start state is the predecessor's end state"""
+    import numpy as np
+    from urh_b200.dist import resolve_psk_chain
+
+    k = lambda a, b: np.array([a, b], np.float32).tobytes()  # noqa: E731
+    hyps = [[(k(0, 1.5), k(1, 2))],
+            [(k(9, 9), k(3, 3)), (k(1, 2), k(4, 4))],
+            [(k(4, 4), k(5, 5)), (k(0, 0), k(6, 6))]]
+    assert resolve_psk_chain(hyps) == ([0, 1, 0], 3)
+    hyps[2][0] = (k(7, 7), k(5, 5))               # shard 2 starts in no hypothesis' state: hand-over from shard 2 on
+    assert resolve_psk_chain(hyps) == ([0, 1], 2)
+    hyps[1] = [(k(-0.0, 2), k(3, 3))]             # -0.0 != +0.0 bitwise... and 1 != -0: unresolved from shard 1
+    assert resolve_psk_chain(hyps) == ([0], 1)
+    assert resolve_psk_chain(hyps[:1]) == ([0], 1)

@@ -85,6 +85,7 @@ SIGNATURES = {
     "urh_center_histogram": (i32, [vp, vp, i64, i64, i64, C.c_double, C.c_double, i64, vp]),
     "urh_afp_demod_tiles": (i32, [vp, vp, i32, i64, f32, i32, vp, i32, vp]),
     "urh_center_window_stats": (i32, [vp, vp, i64, i64, i64, vp]),
+    "urh_center_window_var": (i32, [vp, vp, i64, i64, i64, vp]),
     "urh_center_histogram_tiles": (i32, [vp, vp, i64, i64, i64, C.c_double, C.c_double, i64, vp]),
     "urh_segment_messages": (i32, [vp, vp, i32, i64, f32, vp, i64, C.POINTER(i64)]),
     "urh_plateau_lengths": (i32, [vp, vp, i64, f32, i32, vp, i64, C.POINTER(i64)]),
@@ -132,6 +133,8 @@ SIGNATURES = {
     "urh_nccl_gatherv": (i32, [vp, vp, vp, vp, i32]),
     "urh_set_profiling": (i32, [vp, i32]),
     "urh_last_dense_ms": (i32, [vp, C.POINTER(f32)]),
+    "urh_costas_shard_hypotheses": (i32, [vp, vp, C.POINTER(i32)]),
+    "urh_costas_shard_adopt": (i32, [vp, i32, vp]),
     "urh_costas_stats": (i32, [vp, vp]),
     "urh_costas_last_redone": (i64, [vp]),
     "urh_selftest_packed_div": (i32, [vp, C.c_uint64, i64, C.POINTER(i64), C.POINTER(i64)]),

@@ -201,8 +201,8 @@ def detect_modulation_for_messages(signal, message_indices: list) -> str:
 def detect_center(rectangular_signal, max_size=None):
     """Histogram peak pair of the demodulated signal.  Sample-rate part on the GPU: rank trimming of the
     non-noise samples, min/max/variance, histogram; peak picking (a few thousand bins) on the host.
-    The variance is accumulated in double on the GPU where numpy uses pairwise float32 sums (relative
-    difference ~1e-7); the result agrees with the reference to ~1e-6 relative."""
+    np.var's float32 pairwise sums are replayed bit for bit on the device (pairwise.cu), so bin edges, histogram and center
+    are bit-identical to the reference's."""
     on_device = isinstance(rectangular_signal, DeviceArray)
     n = len(rectangular_signal)
     if n == 0:
@@ -270,7 +270,7 @@ def _center_from_stats(ctx, d, n, st, histogram_entry):
     return pick_center_from_histogram(y, edges)
 
 
-def demod_detect_center(iq, noise_mag: float, mod_type: str, max_size=None, out=None):
+def demod_detect_center(iq, noise_mag: float, mod_type: str, max_size=None, out=None, bitwise=False):
     """afp_demod (ASK/FSK) + detect_center sharing ONE pass over the IQ samples: the demodulator leaves per-tile
     {count, min, max, sum, sumsq} of the kept samples, so detect_center only adds its histogram pass over qad.
     Returns (qad DeviceArray, center or None); same values as afp_demod followed by detect_center.
@@ -294,6 +294,12 @@ def demod_detect_center(iq, noise_mag: float, mod_type: str, max_size=None, out=
     w = np.zeros(5, dtype=np.float64)
     ctx.check(ctx.lib.urh_center_window_stats(ctx.handle, C.c_void_p(qad.ptr), n, r0, r1, w.ctypes.data_as(C.c_void_p)))
     st = center_stats_from_window(kept.value, r0, r1, w)
+    if bitwise and r1 > r0:
+        # np.var(rect) as numpy computes it (float32 pairwise sums replayed on the device): two more passes over the window,
+        # and the center is bit-identical to the reference's instead of agreeing to ~1e-6
+        mv = np.zeros(2, dtype=np.float64)
+        ctx.check(ctx.lib.urh_center_window_var(ctx.handle, C.c_void_p(qad.ptr), n, r0, r1, mv.ctypes.data_as(C.c_void_p)))
+        st[5], st[6] = mv[0], mv[1]
     return qad, _center_from_stats(ctx, qad, n, st, ctx.lib.urh_center_histogram_tiles)
 
 

@@ -15,6 +15,10 @@
 #include "scan.cuh"
 
 #include <math.h>
+#include <stdlib.h>
+
+int urh_window_var_bitwise(urh_ctx* ctx, const float* d_x, int64_t n, const int64_t* d_prefix, int64_t t0, int64_t t1, int64_t r0,
+                           int64_t r1, float* h_out2);   // pairwise.cu
 
 struct CenStats {
     double sum, sumsq;
@@ -31,6 +35,7 @@ k_tile_stats_f32(const float* __restrict__ x, int64_t n, int64_t ntiles, UrhTile
     const int64_t base = tile * URH_TILE;
     UrhStatAcc acc;
     acc.init();
+    acc.all_noise = false;   // not tracked on this path (the sentinel depends on the modulation)
     if (base + URH_TILE <= n && (((uintptr_t)x) & 15) == 0) {
         const float4* p = (const float4*)(x + base) + lane;
         constexpr int ITERS = URH_TILE / 128;
@@ -237,6 +242,19 @@ extern "C" int urh_center_window_stats(urh_ctx* ctx, const float* d_qad, int64_t
     return URH_OK;
 }
 
+// np.mean / np.var of the window [r0, r1) exactly as numpy computes them for a float32 array (pairwise.cu); needs the tile
+// table of the same array in the arena.  h_out2 = {mean, var} (float32 values widened to double).
+extern "C" int urh_center_window_var(urh_ctx* ctx, const float* d_qad, int64_t n, int64_t r0, int64_t r1, double* h_out2) {
+    h_out2[0] = h_out2[1] = 0.0;
+    if (!tiles_match(ctx, d_qad, n)) URH_FAIL(ctx, URH_ERR_INVALID, "the tile table of this array must precede urh_center_window_var");
+    if (r1 <= r0) return URH_OK;
+    float mv[2];
+    URH_CHECK(urh_window_var_bitwise(ctx, d_qad, n, (const int64_t*)ctx->center_prefix, 0, urh_div_up(n, URH_TILE) - 1, r0, r1, mv));
+    h_out2[0] = (double)mv[0];
+    h_out2[1] = (double)mv[1];
+    return URH_OK;
+}
+
 // Stage 1 of the stand-alone detect_center: h_out = {count_valid, r0, r1, min, max, mean, var} of the rank-trimmed samples.
 // Leaves the tile table in the arena for urh_center_histogram on the same array.
 extern "C" int urh_center_stats(urh_ctx* ctx, const float* d_x, int64_t n, int64_t max_size, double* h_out) {
@@ -252,11 +270,20 @@ extern "C" int urh_center_stats(urh_ctx* ctx, const float* d_x, int64_t n, int64
     double w[5];
     URH_CHECK(urh_center_window_stats(ctx, d_x, n, r0, r1, w));
     if (w[0] <= 0.0) return URH_OK;
-    // population variance from the double sums (np.var semantics; the reference's float32 pairwise result differs ~1e-7)
+    h_out[3] = w[1]; h_out[4] = w[2];
+    if (!getenv("URH_B200_CENTER_DOUBLE")) {
+        // np.var(rect) replayed bit for bit (pairwise.cu): numpy's float32 pairwise sums, float32 deviations
+        float mv[2];
+        URH_CHECK(urh_window_var_bitwise(ctx, d_x, n, (const int64_t*)ctx->center_prefix, 0, urh_div_up(n, URH_TILE) - 1, r0, r1, mv));
+        h_out[5] = (double)mv[0];
+        h_out[6] = (double)mv[1];
+        return URH_OK;
+    }
+    // population variance from the double sums (np.var semantics; numpy's float32 pairwise result differs ~1e-7)
     const double mean = w[3] / w[0];
     double ss = w[4] - w[0] * mean * mean;
     if (ss < 0.0) ss = 0.0;
-    h_out[3] = w[1]; h_out[4] = w[2]; h_out[5] = mean; h_out[6] = ss / w[0];
+    h_out[5] = mean; h_out[6] = ss / w[0];
     return URH_OK;
 }
 
@@ -383,7 +410,8 @@ __device__ __forceinline__ void hist_flush(HistCache& hc, unsigned int* s_hist, 
 template <bool SMEM, bool FAST>
 __device__ __forceinline__ void hist_interior_body(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ win,
                                                    const float* __restrict__ g_fe, float scale, int nbins,
-                                                   unsigned long long* __restrict__ hist, int edges_in_smem) {
+                                                   unsigned long long* __restrict__ hist, int edges_in_smem,
+                                                   const int64_t* __restrict__ prefix) {
     extern __shared__ unsigned int s_dyn[];
     unsigned int* s_hist = s_dyn;                               // [nbins] when SMEM
     float* s_fe = (float*)(s_dyn + (SMEM ? nbins : 0));         // [nbins + 3] when edges_in_smem
@@ -403,6 +431,7 @@ __device__ __forceinline__ void hist_interior_body(const float* __restrict__ x, 
     const bool vec = (((uintptr_t)x) & 15) == 0;
     if (win[0] >= 0) {   // < 0: empty window
         for (int64_t t = t_first + gw; t < t_end; t += nw) {
+            if (prefix[t + 1] == prefix[t]) continue;   // no kept sample in this tile (silence): nothing to count, nothing to read
             const int64_t base = t * URH_TILE;   // interior tiles are full tiles (t < last tile)
             if (vec) {
                 const float4* p = (const float4*)(x + base) + lane;
@@ -442,8 +471,9 @@ __device__ __forceinline__ void hist_interior_body(const float* __restrict__ x, 
 template <bool SMEM, bool FAST>
 __global__ void __launch_bounds__(256, 4) k_hist_interior(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ win,
                                                       const float* __restrict__ g_fe, float scale, int nbins,
-                                                      unsigned long long* __restrict__ hist, int edges_in_smem) {
-    hist_interior_body<SMEM, FAST>(x, n, win, g_fe, scale, nbins, hist, edges_in_smem);
+                                                      unsigned long long* __restrict__ hist, int edges_in_smem,
+                                                      const int64_t* __restrict__ prefix) {
+    hist_interior_body<SMEM, FAST>(x, n, win, g_fe, scale, nbins, hist, edges_in_smem, prefix);
 }
 
 // the window's first and last tile (win[0], win[1]; one block each): rank-exact, straight to the global histogram
@@ -505,9 +535,9 @@ extern "C" int urh_center_histogram_tiles(urh_ctx* ctx, const float* d_qad, int6
         const unsigned gs = (unsigned)min(urh_div_up(ntiles, 8), (int64_t)ctx->sm_count * 8);
         const int64_t* cw = d_win;
         const float* cfe = fe;
-        if (in_smem && fast) URH_LAUNCH(ctx, (k_hist_interior<true, true>), gs, 256, dyn, d_qad, n, cw, cfe, scale, (int)nbins, hist, edges_smem);
-        else if (in_smem) URH_LAUNCH(ctx, (k_hist_interior<true, false>), gs, 256, dyn, d_qad, n, cw, cfe, scale, (int)nbins, hist, edges_smem);
-        else URH_LAUNCH(ctx, (k_hist_interior<false, false>), gs, 256, dyn, d_qad, n, cw, cfe, scale, (int)nbins, hist, edges_smem);
+        if (in_smem && fast) URH_LAUNCH(ctx, (k_hist_interior<true, true>), gs, 256, dyn, d_qad, n, cw, cfe, scale, (int)nbins, hist, edges_smem, prefix);
+        else if (in_smem) URH_LAUNCH(ctx, (k_hist_interior<true, false>), gs, 256, dyn, d_qad, n, cw, cfe, scale, (int)nbins, hist, edges_smem, prefix);
+        else URH_LAUNCH(ctx, (k_hist_interior<false, false>), gs, 256, dyn, d_qad, n, cw, cfe, scale, (int)nbins, hist, edges_smem, prefix);
         URH_LAUNCH(ctx, k_hist_window_ends, 2, 256, 0, d_qad, n, prefix, (const int64_t*)d_win, r0, r1, (const float*)fe, scale, (int)nbins, hist);
     }
     URH_CUDA(ctx, cudaMemcpyAsync(h_hist, hist, (size_t)nbins * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -745,9 +775,10 @@ __global__ void __launch_bounds__(256) k_center_plan(const CenStats* __restrict_
 
 template <bool FAST>
 __global__ void __launch_bounds__(256, 4) k_hist_interior_dev(const float* __restrict__ x, int64_t n, const CenterPlan* __restrict__ plan,
-                                                          const float* __restrict__ g_fe, unsigned long long* __restrict__ hist) {
+                                                          const float* __restrict__ g_fe, unsigned long long* __restrict__ hist,
+                                                          const int64_t* __restrict__ prefix) {
     if (plan->state != 1 || (plan->fast != 0) != FAST) return;
-    hist_interior_body<true, FAST>(x, n, (const int64_t*)plan->win, g_fe, plan->scale, (int)plan->nbins, hist, 1);
+    hist_interior_body<true, FAST>(x, n, (const int64_t*)plan->win, g_fe, plan->scale, (int)plan->nbins, hist, 1, prefix);
 }
 __global__ void __launch_bounds__(256) k_hist_window_ends_dev(const float* __restrict__ x, int64_t n, const int64_t* __restrict__ prefix,
                                                              const CenterPlan* __restrict__ plan, const float* __restrict__ g_fe,
@@ -891,8 +922,8 @@ int urh_center_chain(urh_ctx* ctx, const float* d_qad, int64_t n, const UrhTileS
     URH_LAUNCH(ctx, k_center_plan, 1, 256, 0, parts, world, plan, fe, hist);
     const size_t dyn = (size_t)CEN_MAX_BINS * 4 + (size_t)(CEN_MAX_BINS + 3) * 4;   // histogram + edge table, 48 KB
     const unsigned gs = (unsigned)min(urh_div_up(ntiles, 8), (int64_t)ctx->sm_count * 8);
-    URH_LAUNCH(ctx, (k_hist_interior_dev<true>), gs, 256, dyn, d_qad, n, (const CenterPlan*)plan, (const float*)fe, hist);
-    URH_LAUNCH(ctx, (k_hist_interior_dev<false>), gs, 256, dyn, d_qad, n, (const CenterPlan*)plan, (const float*)fe, hist);
+    URH_LAUNCH(ctx, (k_hist_interior_dev<true>), gs, 256, dyn, d_qad, n, (const CenterPlan*)plan, (const float*)fe, hist, (const int64_t*)prefix);
+    URH_LAUNCH(ctx, (k_hist_interior_dev<false>), gs, 256, dyn, d_qad, n, (const CenterPlan*)plan, (const float*)fe, hist, (const int64_t*)prefix);
     URH_LAUNCH(ctx, k_hist_window_ends_dev, 2, 256, 0, d_qad, n, (const int64_t*)prefix, (const CenterPlan*)plan, (const float*)fe, hist);
     if (world > 1) URH_CHECK(urh_nccl_allreduce_i64(ctx, (int64_t*)hist, CEN_MAX_BINS, 0));
     URH_LAUNCH(ctx, k_center_pick, 1, 256, 0, (const unsigned long long*)hist, plan);

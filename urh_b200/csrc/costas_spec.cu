@@ -375,11 +375,20 @@ __global__ void __launch_bounds__(32) k_cs_stitch(const void* __restrict__ iq, i
                                                   const int64_t* __restrict__ prev_live, const CsState* __restrict__ end_a,
                                                   const CsState* __restrict__ end_b, const int64_t* __restrict__ acc_a,
                                                   const int64_t* __restrict__ acc_b, uint8_t* __restrict__ chosen,
-                                                  int64_t* __restrict__ stats, CsState st_in, CsState* __restrict__ st_out) {
+                                                  int64_t* __restrict__ stats, CsState st_in, CsState* __restrict__ st_out, int hyp_mode) {
+    // hyp_mode (later shards of a sharded capture): block h hops under the HYPOTHESIS that the shard starts in candidate h's
+    // start state (true whenever the preceding shard ends locked); each hypothesis has its own chosen[] row, counters, end
+    // state and self-run table, so all of them run concurrently and independently of the preceding shard.
     const int lane = threadIdx.x;
+    const int h = blockIdx.x;
+    chosen += (int64_t)h * nsuper;
+    if (stats) stats += 4 * h;
+    if (st_out) st_out += h;
+    const int self_family = 2 * nbr + h;
     int64_t acc[3] = {0, 0, 0};
     int64_t redone = 0;
     CsState st = st_in;
+    if (hyp_mode) st = ckpt[((int64_t)h * nchunks) * (P.segs + 1)];
     int64_t w = 0;
     if (first_shard) {
         if (lane == 0) chosen[0] = 0;
@@ -415,10 +424,10 @@ __global__ void __launch_bounds__(32) k_cs_stitch(const void* __restrict__ iq, i
             st = end_b[w * nbr + k];
             for (int q = 0; q < 3; q++) acc[q] += acc_b[(w * nbr + k) * 3 + q];
         } else {
-            if (lane == 0) chosen[w] = (uint8_t)(2 * nbr);
+            if (lane == 0) chosen[w] = (uint8_t)self_family;
             redone++;
-            st = cs_chain<DT>(iq, n, P, nchunks, nbr, ckpt, nonnoise, chunk_cnt, T.src + (int64_t)(2 * nbr) * T.nseg,
-                              T.segst + (int64_t)(2 * nbr) * T.nseg, first_shard, lo, min(nchunks, lo + T.sup), st, acc);
+            st = cs_chain<DT>(iq, n, P, nchunks, nbr, ckpt, nonnoise, chunk_cnt, T.src + (int64_t)self_family * T.nseg,
+                              T.segst + (int64_t)self_family * T.nseg, first_shard, lo, min(nchunks, lo + T.sup), st, acc);
         }
     }
     if (lane == 0 && st_out) *st_out = st;
@@ -524,6 +533,7 @@ struct CsRun {
     int64_t* stats;
     CsState* st_out;
     float* out;
+    int adopted;   // hypothesis whose chosen[] row / counters the assemble and fix passes use
 };
 
 #define CS_DISPATCH(R, KERNEL, ...)                                                    \
@@ -550,16 +560,19 @@ static int cs_speculate(urh_ctx* ctx, CsRun& R) {
     R.T.nseg = R.nchunks * R.P.segs;
     R.T.sup = (int)max((int64_t)CS_SUP_MIN, urh_div_up((int64_t)131072, (int64_t)R.P.chunk));
     R.nsuper = urh_div_up(R.nchunks, R.T.sup);
-    URH_CHECK(urh_arena(ctx, (size_t)(2 * R.nbr + 1) * R.T.nseg, &R.T.src));
-    URH_CHECK(urh_arena(ctx, (size_t)(2 * R.nbr + 1) * R.T.nseg, &R.T.segst));
+    // table families: nbr x A, nbr x B, then one self-run table per stitch hypothesis (a single one when unsharded)
+    const int self_tables = R.first_shard ? 1 : R.nbr;
+    URH_CHECK(urh_arena(ctx, (size_t)(2 * R.nbr + self_tables) * R.T.nseg, &R.T.src));
+    URH_CHECK(urh_arena(ctx, (size_t)(2 * R.nbr + self_tables) * R.T.nseg, &R.T.segst));
     URH_CHECK(urh_arena(ctx, (size_t)2 * R.nsuper * R.nbr, &R.sup_end));
     URH_CHECK(urh_arena(ctx, (size_t)2 * R.nsuper * R.nbr * 3, &R.sup_acc));
     URH_CHECK(urh_arena(ctx, (size_t)R.nsuper, &R.live));
     URH_CHECK(urh_arena(ctx, (size_t)R.nsuper, &R.prev_live));
-    URH_CHECK(urh_arena(ctx, (size_t)R.nsuper, &R.chosen));
+    URH_CHECK(urh_arena(ctx, (size_t)R.nsuper * self_tables, &R.chosen));
     URH_CHECK(urh_arena(ctx, (size_t)R.nchunks, &R.chunk_cnt));
-    URH_CHECK(urh_arena(ctx, 4, &R.stats));
-    URH_CHECK(urh_arena(ctx, 2, &R.st_out));
+    URH_CHECK(urh_arena(ctx, (size_t)4 * self_tables, &R.stats));
+    URH_CHECK(urh_arena(ctx, (size_t)2 * self_tables, &R.st_out));
+    R.adopted = 0;
     const dim3 grid((unsigned)urh_div_up(R.nchunks, 128), (unsigned)R.nbr);
     CS_DISPATCH(R, k_cs_speculate, grid, 128, 0, R.iq, R.n, R.P, R.nchunks, R.cand, R.ckpt, R.nonnoise, R.chunk_cnt, R.first_shard);
     // pass 2a: the chains of every super-chunk under every assumption (independent of the true incoming state)
@@ -575,24 +588,36 @@ static int cs_speculate(urh_ctx* ctx, CsRun& R) {
     return URH_OK;
 }
 
-static int cs_resolve(urh_ctx* ctx, CsRun& R, CsState st_in, float* h_state_out) {
-    const int64_t per = R.nsuper * R.nbr;
-    CS_DISPATCH(R, k_cs_stitch, 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.T, R.first_shard, R.nsuper,
-                (const int64_t*)R.prev_live, (const CsState*)R.sup_end, (const CsState*)(R.sup_end + per), (const int64_t*)R.sup_acc,
-                (const int64_t*)(R.sup_acc + per * 3), R.chosen, R.stats, st_in, R.st_out);
+// assemble + fix with hypothesis R.adopted's chosen[] row; returns that run's end state
+static int cs_finish(urh_ctx* ctx, CsRun& R, float* h_state_out) {
+    const uint8_t* chosen = R.chosen + (int64_t)R.adopted * R.nsuper;
     const unsigned ga = (unsigned)min(urh_div_up(R.n, 256), (int64_t)ctx->sm_count * 32);
-    URH_LAUNCH(ctx, k_cs_assemble, ga, 256, 0, R.cand, R.n, R.T, R.P.segs, R.chosen, R.out);
-    CS_DISPATCH(R, k_cs_fix, (unsigned)min(urh_div_up(R.T.nseg * 32, 128), (int64_t)ctx->sm_count * 16), 128, 0, R.iq, R.n, R.P, R.T, R.chosen,
+    URH_LAUNCH(ctx, k_cs_assemble, ga, 256, 0, R.cand, R.n, R.T, R.P.segs, chosen, R.out);
+    CS_DISPATCH(R, k_cs_fix, (unsigned)min(urh_div_up(R.T.nseg * 32, 128), (int64_t)ctx->sm_count * 16), 128, 0, R.iq, R.n, R.P, R.T, chosen,
                 R.first_shard, R.out);
     int64_t st4[4];
-    URH_CHECK(urh_read_i64(ctx, R.stats, 4, st4));
+    URH_CHECK(urh_read_i64(ctx, R.stats + 4 * R.adopted, 4, st4));
     for (int i = 0; i < 3; i++) ctx->costas_stats[i] = st4[i];
     ctx->costas_redone = st4[3];
     if (h_state_out) {
-        URH_CUDA(ctx, cudaMemcpyAsync(h_state_out, R.st_out, sizeof(CsState), cudaMemcpyDeviceToHost, ctx->stream));
+        URH_CUDA(ctx, cudaMemcpyAsync(h_state_out, R.st_out + R.adopted, sizeof(CsState), cudaMemcpyDeviceToHost, ctx->stream));
         URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return URH_OK;
+}
+
+static int cs_stitch(urh_ctx* ctx, CsRun& R, CsState st_in, int hypotheses) {
+    const int64_t per = R.nsuper * R.nbr;
+    CS_DISPATCH(R, k_cs_stitch, hypotheses > 0 ? hypotheses : 1, 32, 0, R.iq, R.n, R.P, R.nchunks, R.nbr, R.ckpt, R.nonnoise, R.chunk_cnt, R.T,
+                R.first_shard, R.nsuper, (const int64_t*)R.prev_live, (const CsState*)R.sup_end, (const CsState*)(R.sup_end + per),
+                (const int64_t*)R.sup_acc, (const int64_t*)(R.sup_acc + per * 3), R.chosen, R.stats, st_in, R.st_out, hypotheses > 0 ? 1 : 0);
+    return URH_OK;
+}
+
+static int cs_resolve(urh_ctx* ctx, CsRun& R, CsState st_in, float* h_state_out) {
+    URH_CHECK(cs_stitch(ctx, R, st_in, 0));
+    R.adopted = 0;
+    return cs_finish(ctx, R, h_state_out);
 }
 
 int urh_costas_demod(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_sqrd, int loop_order, float bandwidth,
@@ -634,6 +659,37 @@ extern "C" int urh_costas_shard_resolve(urh_ctx* ctx, const float* h_state_in, f
     in.freq = h_state_in ? h_state_in[0] : 0.f;
     in.phase = h_state_in ? h_state_in[1] : 1.5f;
     return cs_resolve(ctx, g_shard_run, in, h_state_out);
+}
+
+// Later shards: hop over the shard under each of the `order` hypotheses "the shard starts in candidate h's start state",
+// all at once (one warp each), independent of the preceding shard.  h_out[h] = {start.freq, start.phase, end.freq, end.phase}.
+// The first shard has one true run: h_out[0] = {initial state, end state}.  Returns the number of hypotheses in *count.
+extern "C" int urh_costas_shard_hypotheses(urh_ctx* ctx, float* h_out, int* count) {
+    CsRun& R = g_shard_run;
+    const int nh = R.first_shard ? 1 : R.nbr;
+    CsState none;
+    none.freq = 0.f; none.phase = 1.5f;
+    URH_CHECK(cs_stitch(ctx, R, none, R.first_shard ? 0 : nh));
+    CsState ends[4], starts[4];
+    URH_CUDA(ctx, cudaMemcpyAsync(ends, R.st_out, sizeof(CsState) * nh, cudaMemcpyDeviceToHost, ctx->stream));
+    for (int h = 0; h < nh && !R.first_shard; h++)
+        URH_CUDA(ctx, cudaMemcpyAsync(&starts[h], R.ckpt + ((int64_t)h * R.nchunks) * (R.P.segs + 1), sizeof(CsState), cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (R.first_shard) starts[0] = none;
+    for (int h = 0; h < nh; h++) {
+        h_out[4 * h + 0] = starts[h].freq; h_out[4 * h + 1] = starts[h].phase;
+        h_out[4 * h + 2] = ends[h].freq; h_out[4 * h + 3] = ends[h].phase;
+    }
+    *count = nh;
+    return URH_OK;
+}
+
+// Adopt hypothesis h (its start state equalled, bit for bit, the preceding shard's end state): assemble + fix.
+extern "C" int urh_costas_shard_adopt(urh_ctx* ctx, int h, float* h_state_out) {
+    CsRun& R = g_shard_run;
+    if (h < 0 || h >= (R.first_shard ? 1 : R.nbr)) URH_FAIL(ctx, URH_ERR_INVALID, "costas_shard_adopt: no such hypothesis");
+    R.adopted = h;
+    return cs_finish(ctx, R, h_state_out);
 }
 
 // diagnostics of the last speculative run: {chunks resolved in O(1), chunks walked, samples stepped serially}

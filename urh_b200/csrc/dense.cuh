@@ -40,14 +40,16 @@ struct __align__(16) UrhTileSummary {
 struct __align__(16) UrhTileStats {
     double sum, sumsq;
     float mn, mx;
-    int32_t cnt, pad;
+    int32_t cnt;
+    int32_t all_noise;   // 1: every sample of the tile equals the NOISE sentinel (the digitizer's class -1 throughout)
 };
 
 struct UrhStatAcc {
     double sum, sumsq;
     float mn, mx;
     int cnt;
-    __device__ __forceinline__ void init() { sum = 0.0; sumsq = 0.0; mn = INFINITY; mx = -INFINITY; cnt = 0; }
+    bool all_noise;
+    __device__ __forceinline__ void init() { sum = 0.0; sumsq = 0.0; mn = INFINITY; mx = -INFINITY; cnt = 0; all_noise = true; }
     __device__ __forceinline__ void add(float v) {
         if (v > -4.0f) {
             const double d = (double)v;
@@ -67,9 +69,10 @@ struct UrhStatAcc {
             mx = fmaxf(mx, __shfl_down_sync(URH_FULL_MASK, mx, off));
             cnt += __shfl_down_sync(URH_FULL_MASK, cnt, off);
         }
+        const int alln = __all_sync(URH_FULL_MASK, all_noise) ? 1 : 0;
         if (lane == 0) {
             UrhTileStats t;
-            t.sum = sum; t.sumsq = sumsq; t.mn = mn; t.mx = mx; t.cnt = cnt; t.pad = 0;
+            t.sum = sum; t.sumsq = sumsq; t.mn = mn; t.mx = mx; t.cnt = cnt; t.all_noise = alln;
             *out = t;
         }
     }

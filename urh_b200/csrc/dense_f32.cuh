@@ -29,7 +29,8 @@ template <typename SRC, typename T>
 __global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32)
 k_dense_f32(const T* __restrict__ x, int64_t n, int vec_in, const __grid_constant__ UrhClassify cls, int tol,
             UrhTileSummary* __restrict__ tiles, uint32_t* __restrict__ staging, int stage_cap,
-            int16_t* __restrict__ init_cls, int cls_of_zero, const float* __restrict__ d_thr0 = nullptr) {
+            int16_t* __restrict__ init_cls, int cls_of_zero, const float* __restrict__ d_thr0 = nullptr,
+            const UrhTileStats* __restrict__ tile_stats = nullptr) {
     // d_thr0: the (binary) threshold lives in device memory (center detected on the device); then cls_of_zero is derived here
     const float thr0 = d_thr0 ? *d_thr0 : cls.thr[0];
     if (d_thr0) cls_of_zero = (0.0f <= thr0) ? 0 : 1;
@@ -39,6 +40,16 @@ k_dense_f32(const T* __restrict__ x, int64_t n, int vec_in, const __grid_constan
     if (tile_start >= n) return;
     const int tile_len = (int)((n - tile_start) < URH_TILE ? (n - tile_start) : URH_TILE);
     const int iters = (tile_len + 63) >> 6;
+    // the demodulator's tile table says the whole tile is NOISE: one run of class -1, nothing to read (captures are mostly silence)
+    if (tile_stats && tile_stats[tile].all_noise) {
+        if (lane == 0) {
+            UrhTileSummary s;
+            s.first_cls = -1; s.last_cls = -1; s.head_len = tile_len; s.tail_len = tile_len; s.ncand = 0;
+            tiles[tile] = s;
+            if (tile_start == 0 && init_cls) *init_cls = (int16_t)-1;
+        }
+        return;
+    }
     UrhRunTracker rt;
     rt.init(tol, staging + tile * (int64_t)stage_cap);
     if (vec_in && tile_len == URH_TILE) {

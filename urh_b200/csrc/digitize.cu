@@ -77,8 +77,8 @@ k_dense_iq(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
 
         const bool v0 = pos0 < n, v1 = pos0 + 1 < n;
         if (tile_stats) {
-            if (v0) acc.add(s0);
-            if (v1) acc.add(s1);
+            if (v0) { acc.add(s0); acc.all_noise = acc.all_noise && (s0 == dp.noise_value); }
+            if (v1) { acc.add(s1); acc.all_noise = acc.all_noise && (s1 == dp.noise_value); }
         }
         if (qad_out) {
             if (v1 && vec_out) urh_stg_f2(qad_out + pos0, s0, s1);
@@ -571,7 +571,7 @@ static int demod_center_digitize_impl(urh_ctx* ctx, const void* d_iq, int dtype,
     URH_CUDA(ctx, cudaMemsetAsync(d_init, 0, 16, ctx->stream));
     const int vec_in = (((uintptr_t)d_qad_out % 8) == 0) ? 1 : 0;
     URH_LAUNCH(ctx, (k_dense_f32<SrcQad2, float>), (unsigned)urh_div_up(ntiles, URH_WARPS_PER_BLOCK), URH_WARPS_PER_BLOCK * 32, 0,
-               (const float*)d_qad_out, n, vec_in, cls, tol, tiles, staging, cap, d_init, 0, d_centerf);
+               (const float*)d_qad_out, n, vec_in, cls, tol, tiles, staging, cap, d_init, 0, d_centerf, (const UrhTileStats*)ts);
     URH_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 40, d_center, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     URH_CUDA(ctx, cudaMemcpyAsync(ctx->h_mail + 41, d_state, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     int64_t rows = 0;

@@ -17,8 +17,6 @@
 namespace urhts {
 
 constexpr int BLOCK = 256;
-constexpr int ITEMS = 4;
-constexpr int CHUNK = BLOCK * ITEMS;
 constexpr int SLOT = 32;  // bytes reserved per published value (sizeof(T) <= SLOT, multiple of 4)
 
 struct Ws {
@@ -79,8 +77,11 @@ __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <typename T, typename Op, typename F>
+// ITEMS consecutive elements per thread.  The look-back chain advances 32 blocks per global-memory round trip, so few, fat
+// blocks finish sooner than many thin ones on tables of this size (2^19 tiles: 128 blocks at ITEMS = 16).
+template <typename T, typename Op, typename F, int ITEMS>
 __global__ void __launch_bounds__(BLOCK) k_scan(int64_t n, T identity, Op op, F f, Ws ws, T* __restrict__ total_out) {
+    constexpr int CHUNK = BLOCK * ITEMS;
     __shared__ unsigned long long s_bid;
     __shared__ T s_warp[BLOCK / 32];
     __shared__ T s_block_excl;
@@ -173,13 +174,13 @@ __global__ void __launch_bounds__(BLOCK) k_scan(int64_t n, T identity, Op op, F 
 // host side (context.cu): workspace for `nblocks` blocks of the next launch
 int prepare(urh_ctx* ctx, int64_t nblocks, Ws* out);
 
-template <typename T, typename Op, typename F>
+template <typename T, typename Op, typename F, int ITEMS = 16>
 static inline int scan(urh_ctx* ctx, int64_t n, T identity, Op op, F f, T* d_total) {
     if (n <= 0) return URH_OK;
-    const int64_t nb = urh_div_up(n, CHUNK);
+    const int64_t nb = urh_div_up(n, (int64_t)BLOCK * ITEMS);
     Ws ws;
     URH_CHECK(prepare(ctx, nb, &ws));
-    URH_LAUNCH(ctx, (k_scan<T, Op, F>), (unsigned)nb, BLOCK, 0, n, identity, op, f, ws, d_total);
+    URH_LAUNCH(ctx, (k_scan<T, Op, F, ITEMS>), (unsigned)nb, BLOCK, 0, n, identity, op, f, ws, d_total);
     return URH_OK;
 }
 

@@ -146,23 +146,68 @@ def costas_halo(ctx) -> int:
     return int(ctx.lib.urh_costas_halo_samples())
 
 
+def resolve_psk_chain(hyps):
+    """Pure host logic of the sharded Costas loop (unit-tested on the CPU).  ``hyps[r]`` = list of (start_state, end_state) per
+    hypothesis of rank r, states as raw 8-byte keys; rank 0 has one entry (its true run).  Returns (picks, first_unresolved):
+    picks[r] = hypothesis of rank r whose start state equals the true end state of rank r-1, for r < first_unresolved;
+    first_unresolved = world when every shard is resolved."""
+    picks = [0]
+    state = hyps[0][0][1]
+    for r in range(1, len(hyps)):
+        match = [h for h, (start, _) in enumerate(hyps[r]) if start == state]
+        if not match:
+            return picks, r
+        picks.append(match[0])
+        state = hyps[r][match[0]][1]
+    return picks, len(hyps)
+
+
 def afp_demod_psk_sharded(ctx, rank, world, sb: ShardBuffer, noise_mag, mod_order, costas_loop_bandwidth, d_out):
-    """PSK demodulation (Costas loop) of a capture sharded over the ranks, bit-identical to the serial loop.  Every
-    rank speculates over its shard concurrently (the expensive pass); the loop state is then handed from rank to rank
-    (one 8-byte NCCL all-gather per rank) for the cheap chain-resolution pass.  sb needs a halo of costas_halo() samples."""
+    """PSK demodulation (Costas loop) of a capture sharded over the ranks, bit-identical to the serial loop.  Every rank
+    speculates over its shard concurrently (the expensive pass) AND hops over it under each hypothesis "my shard starts in
+    candidate h's start state" — what a locked loop of the preceding shard ends in, bit for bit.  One all-gather of
+    (start, end) state pairs lets every rank pick its hypothesis (``resolve_psk_chain``); nothing waits for a neighbour.
+    Only a shard whose predecessor ends in no hypothesis' start state (it begins inside a gap that carries a frozen or creeping
+    loop state) falls back to the rank-to-rank hand-over from that shard on.  sb needs a halo of costas_halo() samples."""
     lib = ctx.lib
     assert rank == 0 or sb.halo_len >= costas_halo(ctx)
     ctx.check(lib.urh_costas_shard_speculate(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, int(rank == 0),
                                              float(noise_mag), int(mod_order), float(costas_loop_bandwidth), C.c_void_p(d_out.ptr)))
+    mine = np.zeros((4, 4), dtype=np.float32)
+    count = C.c_int(0)
+    ctx.check(lib.urh_costas_shard_hypotheses(ctx.handle, mine.ctypes.data_as(C.c_void_p), C.byref(count)))
+    mine[count.value:] = np.nan
+    payload = np.concatenate([mine.reshape(-1).view(np.int32).astype(np.int64), [count.value]]).astype(np.int64)
+    every = nccl_allgather_wide(ctx, world, payload)
+    hyps = []
+    for r in range(world):
+        cnt = int(every[r, -1])
+        raw = every[r, :16].astype(np.int32).view(np.float32).reshape(4, 4)
+        hyps.append([(raw[h, 0:2].tobytes(), raw[h, 2:4].tobytes()) for h in range(cnt)])
+    picks, unresolved = resolve_psk_chain(hyps)
     state = np.zeros(2, dtype=np.float32)
-    for turn in range(world):
-        mine = np.zeros(2, dtype=np.float32)
-        if turn == rank:
-            ctx.check(lib.urh_costas_shard_resolve(ctx.handle, state.ctypes.data_as(C.c_void_p), mine.ctypes.data_as(C.c_void_p)))
-        every = np.empty((world, 2), dtype=np.float32)
-        ctx.check(lib.urh_nccl_allgather_host(ctx.handle, mine.ctypes.data_as(C.c_void_p), every.ctypes.data_as(C.c_void_p), mine.nbytes))
-        state = every[turn].copy()  # the loop state at the end of shard `turn`
+    if rank < unresolved:
+        ctx.check(lib.urh_costas_shard_adopt(ctx.handle, picks[rank], state.ctypes.data_as(C.c_void_p)))
+    if unresolved < world:
+        # hand-over from the first unresolved shard on: its predecessor's end state is known exactly
+        carry = np.frombuffer(hyps[unresolved - 1][picks[unresolved - 1]][1], dtype=np.float32).copy()
+        for turn in range(unresolved, world):
+            out = np.zeros(2, dtype=np.float32)
+            if turn == rank:
+                ctx.check(lib.urh_costas_shard_resolve(ctx.handle, carry.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+                state = out
+            allv = np.empty((world, 2), dtype=np.float32)
+            ctx.check(lib.urh_nccl_allgather_host(ctx.handle, out.ctypes.data_as(C.c_void_p), allv.ctypes.data_as(C.c_void_p), out.nbytes))
+            carry = allv[turn].copy()
     return state
+
+
+def nccl_allgather_wide(ctx, world, values):
+    """all-gather an int64 vector per rank over NCCL (pinned staging) -> array [world, len(values)]"""
+    send = np.ascontiguousarray(values, dtype=np.int64)
+    recv = np.empty((world, len(send)), dtype=np.int64)
+    ctx.check(ctx.lib.urh_nccl_allgather_host(ctx.handle, send.ctypes.data_as(C.c_void_p), recv.ctypes.data_as(C.c_void_p), send.nbytes))
+    return recv
 
 
 def demod_digitize_sharded(ctx, hx, sb: ShardBuffer, global_offset, n_total, noise_mag, mod_type, center, tolerance,
