@@ -275,6 +275,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--worst", action="store_true",
+                    help="also time the unfavourable inputs (noise gate off / white-noise IQ / +-300 kHz deviation: every sample pair "
+                         "leaves the packed-f32x2 fast path) and report them under `worst_case`")
     args = ap.parse_args()
 
     rank = env_int("RANK", 0)
@@ -543,6 +546,36 @@ def main():
         assert lens == n_total - TOL, (lens, n_total - TOL)
         host.free()
 
+    # ---- the unfavourable inputs (same kernel entry points, same timing rules, fewer steps) -----------------------------------
+    worst = None
+    if args.worst and world == 1:
+        worst = []
+        cases = [("noise gate off (noise_mag = 0): no sample is skipped", FDEV / FS, 1.0, SIGMA, 0.0),
+                 ("+-300 kHz deviation (0.94 rad/sample): |im/re| >= 0.4375 for every pair -> scalar bit-exact atan2f path", 0.15, 1.0, SIGMA, NOISE_MAG),
+                 ("white-noise IQ (sigma = 1, no carrier), noise gate off: random angles, ~70 % of the pairs on the scalar path", 0.0, 0.0, 1.0, 0.0)]
+        for name, dev, amp, sigma, noise in cases:
+            ctx.check(lib.urh_synth_fsk(ctx.handle, C.c_void_p(d_iq.ptr), n, offset, SPS, C.c_void_p(d_b.ptr), C.c_void_p(d_s.ptr),
+                                        C.c_double(dev), amp, sigma, 777, period, burst, int(0.40 * n_total), int(0.43 * n_total),
+                                        int(0.97 * n_total)))
+            ctx.sync()
+            k = C.c_int64(0)
+
+            def run():
+                ctx.check(lib.urh_demod_digitize(ctx.handle, C.c_void_p(d_iq.ptr), _lib.DT_F32, n, noise, _lib.MOD_FSK, CENTER, TOL, SPS, 1, 0.1,
+                                                 C.c_void_p(d_qad.ptr), C.byref(k)))
+                return read_dense_ms()
+            for _ in range(3):
+                run()
+            ctx.sync()
+            dms = []
+            ctx.timer_start()
+            for _ in range(10):
+                dms.append(run())
+            ms = ctx.timer_stop() / 10
+            worst.append({"input": name, "step": "fused demod+digitize, center=0 given", "ms_per_step": ms, "value": n / (ms * 1e-3) / 1e6,
+                          "unit": "MSamples/s", "dense_kernel_ms": float(np.mean(dms)), "pulse_rows": int(k.value),
+                          "dense_kernel_GBps": ALG_BYTES_PER_SAMPLE * n / (float(np.mean(dms)) * 1e-3) / 1e9})
+
     if rank != 0:
         return 0
 
@@ -586,7 +619,7 @@ def main():
     line = dict(base)
     line.update({"value": value, "ms_per_step": ms_per_step, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
                  "gpu_launches": int(launches), "clocks": clocks, "pulse_rows_per_step": int(k_rows),
-                 "detected_center": center_seen[0], "other_variant": other_line, "stage_ms": stages,
+                 "detected_center": center_seen[0], "other_variant": other_line, "worst_case": worst, "stage_ms": stages,
                  "device": info["name"], "sm_count": info["sm_count"]})
     print(json.dumps(line))
     return 0

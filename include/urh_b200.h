@@ -119,6 +119,13 @@ int urh_center_histogram_tiles(urh_ctx* ctx, const float* d_qad, int64_t n, int6
 /* replaces auto_interpretation.segment_messages_from_magnitudes (auto_interpretation.pyx:55-111) */
 int urh_segment_messages(urh_ctx* ctx, const void* d_mags, int is_f64, int64_t n, float noise_threshold,
                          int64_t* h_segments, int64_t cap, int64_t* k);
+/* Sharded captures: urh_segment_shard_pass = the dense pass of one shard's magnitudes (then urh_shard_candidates with the run
+ * carry of the preceding shards and urh_fetch_candidates); urh_segments_from_runs = the state machine of
+ * auto_interpretation.pyx:69-111 over the concatenated run table of all shards (pure host code). */
+int urh_segment_shard_pass(urh_ctx* ctx, const void* d_mags, int is_f64, int64_t n, float noise_threshold, int64_t* h_summary);
+int urh_segments_from_runs(const int64_t* h_pos, const int16_t* h_cls, int64_t count, int first_above, int last_cls,
+                           int64_t last_len, int64_t n, int64_t* h_segments, int64_t cap, int64_t* k);
+int urh_fetch_candidates(urh_ctx* ctx, int64_t* h_pos, int16_t* h_cls, int64_t count);
 /* replaces auto_interpretation.get_plateau_lengths (auto_interpretation.pyx:179-208) */
 int urh_plateau_lengths(urh_ctx* ctx, const float* d_rect, int64_t n, float center, int percentage, uint64_t* h_out,
                         int64_t cap, int64_t* k);
@@ -136,6 +143,8 @@ int urh_modulate_batch(urh_ctx* ctx, const uint8_t* d_bits, const int64_t* h_bit
                        uint32_t samples_per_symbol, int mod_type, const float* h_params, int nparams, int bits_per_symbol,
                        float carrier_amplitude, float carrier_frequency, float carrier_phase, float sample_rate,
                        uint32_t start, int out_dtype, const float* h_gauss_fir, int gauss_len, void* d_out);
+/* diagnostics: 32-sample blocks of the GFSK phase recurrence folded as an integer prefix sum / in order since the last call */
+int urh_modulate_stats(urh_ctx* ctx, int64_t* h_out2);
 
 /* ---- filters (filter.cu) ----------------------------------------------------------------------------------
  * urh_fir_filter replaces signal_functions.fir_filter (signal_functions.pyx:513-525), exact accumulation order;
@@ -235,6 +244,8 @@ int urh_nccl_allreduce_f64(urh_ctx* ctx, double* d_buf, int64_t count, int op); 
 int urh_nccl_allreduce_i64(urh_ctx* ctx, int64_t* d_buf, int64_t count, int op);
 int urh_nccl_allgather(urh_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
 int urh_nccl_gatherv(urh_ctx* ctx, const void* d_send, void* d_recv, const int64_t* h_bytes, int root);
+int urh_nccl_sendrecv(urh_ctx* ctx, const void* d_send, size_t send_bytes, int send_peer, void* d_recv, size_t recv_bytes,
+                      int recv_peer);
 int urh_nccl_allgather_host(urh_ctx* ctx, const void* h_send, void* h_recv, size_t bytes_per_rank);
 int urh_nccl_allreduce_host_i64(urh_ctx* ctx, int64_t* h_buf, int64_t count, int op);
 /* the same few-bytes all-gather over NVLink peer memory, one small kernel per rank (p2p.cu): every rank creates a mailbox and
@@ -257,6 +268,8 @@ int urh_selftest_packed_div(urh_ctx* ctx, uint64_t seed, int64_t count, int64_t*
 int urh_synth_fsk(urh_ctx* ctx, float* d_iq, int64_t n, int64_t global_offset, int sps, const int8_t* d_sym_bit,
                   const int32_t* d_sym_sum, double dev_ratio, float amplitude, float sigma, uint64_t seed,
                   int64_t period, int64_t burst, int64_t big_gap_start, int64_t big_gap_end, int64_t tail_start);
+int urh_synth_psk(urh_ctx* ctx, float* d_iq, int64_t n, int64_t global_offset, int sps, int order, double carrier_ratio,
+                  float amplitude, float sigma, uint64_t seed, int64_t period, int64_t burst, int64_t tail_start);
 
 #ifdef __cplusplus
 }

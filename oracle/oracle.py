@@ -60,6 +60,18 @@ def afp_demod(samples, noise_mag, mod_type, mod_order, costas_loop_bandwidth=0.1
     return out
 
 
+def costas_from(samples, noise_mag, loop_order, state, costas_loop_bandwidth=0.1):
+    """The Costas loop (signal_functions.pyx:289-328) over ALL of `samples`, continued from the loop state (freq, phase) a
+    preceding segment ended in -> (demodulated float32, end state).  Checker for captures sharded over GPUs."""
+    samples = np.ascontiguousarray(samples)
+    n = len(samples)
+    out = np.zeros(n, dtype=np.float32)
+    end = np.zeros(2, dtype=np.float32)
+    lib().oracle_costas_from(_p(samples), DT[samples.dtype], C.c_int64(n), C.c_float(noise_mag), int(loop_order),
+                             C.c_float(costas_loop_bandwidth), C.c_float(state[0]), C.c_float(state[1]), _p(out), _p(end))
+    return out, end
+
+
 def get_center_thresholds(center, spacing, order):
     out = np.empty(max(order - 1, 0), dtype=np.float32)
     lib().oracle_center_thresholds(C.c_float(center), C.c_float(spacing), int(order), _p(out))

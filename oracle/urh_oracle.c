@@ -51,7 +51,18 @@ static inline void cmulf(float a, float b, float c, float d, float* re, float* i
 }
 
 /* Costas loop — src/urh/cythonext/signal_functions.pyx:252-330 */
+static void costas_from(const void* iq, int dtype, int64_t n, float noise_sqrd, int loop_order, float bandwidth, float* out,
+                        int64_t first, float freq0, float phase0, float* end_state);
 static void costas(const void* iq, int dtype, int64_t n, float noise_sqrd, int loop_order, float bandwidth, float* out) {
+    if (n > 0) out[0] = 0.0f; /* np.empty in the reference: undefined; we pin it to 0 */
+    costas_from(iq, dtype, n, noise_sqrd, loop_order, bandwidth, out, 1, 0.0f, 1.5f, 0);
+}
+
+/* The loop of signal_functions.pyx:289-328 over samples [first, n), starting from the loop state (freq0, phase0); the state
+ * after the last sample goes to end_state[0..1].  costas() above is the reference's call (first = 1, state 0 / 1.5); a later start
+ * with the state a preceding segment ended in continues that run (test oracle for captures sharded over GPUs). */
+static void costas_from(const void* iq, int dtype, int64_t n, float noise_sqrd, int loop_order, float bandwidth, float* out,
+                        int64_t first, float freq0, float phase0, float* end_state) {
     const float damping = (float)(sqrt(2.0) / 2.0);
     const double den = (1.0 + ((2.0 * damping) * bandwidth)) + (bandwidth * bandwidth);
     const float alpha = (float)(((double)((4.0 * damping) * bandwidth)) / den);
@@ -65,9 +76,8 @@ static void costas(const void* iq, int dtype, int64_t n, float noise_sqrd, int l
         default: scale = 1.0f; shift = 0.0f; break;
     }
     if (loop_order > 4) loop_order = 4;
-    float freq = 0.0f, err = 0.0f, phase = 1.5f;
-    if (n > 0) out[0] = 0.0f; /* np.empty in the reference: undefined; we pin it to 0 */
-    for (int64_t i = 1; i < n; i++) {
+    float freq = freq0, err = 0.0f, phase = phase0;
+    for (int64_t i = first; i < n; i++) {
         const float re = iq_at(iq, dtype, 2 * i), im = iq_at(iq, dtype, 2 * i + 1);
         if (re * re + im * im <= noise_sqrd) {
             out[i] = -4.0f;
@@ -96,6 +106,15 @@ static void costas(const void* iq, int dtype, int64_t n, float noise_sqrd, int l
         if (loop_order == 2) out[i] = xr;
         else if (loop_order == 4) out[i] = (float)((2.0 * xr) + xi);
     }
+    if (end_state) { end_state[0] = freq; end_state[1] = phase; }
+}
+
+/* test hook: continue a Costas run from a known loop state (see costas_from) */
+int oracle_costas_from(const void* iq, int dtype, int64_t n, float noise_mag, int loop_order, float bandwidth, float freq0, float phase0,
+                       float* out, float* end_state) {
+    const float noise_sqrd = noise_mag * noise_mag;
+    costas_from(iq, dtype, n, noise_sqrd, loop_order, bandwidth, out, 0, freq0, phase0, end_state);
+    return 0;
 }
 
 /* afp_demod — src/urh/cythonext/signal_functions.pyx:333-378 */

@@ -99,6 +99,29 @@ def main():
             got = np.concatenate(parts)
             if not np.array_equal(got[1:].view(np.uint32), ref[1:].view(np.uint32)):
                 failures.append(("psk", order, int((got[1:].view(np.uint32) != ref[1:].view(np.uint32)).sum())))
+    # AutoInterpretation.estimate over shards == estimate on one GPU (BASELINE configs[4] shape, small)
+    from urh_b200.signalprocessing.IQArray import IQArray
+    for kind in ("FSK", "PSK"):
+        n = 2_400_000
+        if kind == "FSK":
+            iq = synth_fsk(n, sps=100, seed=91, gap_every=150_000)
+            iq[-60_000:] *= 0.001
+        else:
+            iq = synth_psk(n, 2, seed=92, gap_period=300_000, gap_len=90_000)
+        bounds = udist.shard_bounds(n, world)
+        lo, hi = bounds[rank]
+        sb = udist.ShardBuffer(ctx, hi - lo, np.float32, halo=udist.costas_halo(ctx))
+        sb.shard.set(iq[lo:hi])
+        udist.exchange_halo(ctx, hx, sb)
+        for given in (kind, None):
+            est = udist.estimate_sharded(ctx, hx, sb, bounds, n, noise=None, modulation=given)
+            ests = hx.allgather(est)
+            if rank == 0:
+                one = AI.estimate(IQArray(iq), noise=None, modulation=given)
+                if any(e != ests[0] for e in ests):
+                    failures.append(("estimate differs between ranks", kind, given))
+                if one != est:
+                    failures.append(("estimate", kind, given, est, one))
     res = hx.allgather(failures)
     if rank == 0:
         flat = [f for part in res for f in part]

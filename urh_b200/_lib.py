@@ -113,6 +113,9 @@ SIGNATURES = {
     "urh_shard_demod_center_digitize": (i32, [vp, vp, i32, i64, i32, f32, i32, u16, u32, i64, vp, i64, i64, C.POINTER(C.c_double),
                                               C.POINTER(i32), C.POINTER(i64)]),
     "urh_shard_digitize": (i32, [vp, vp, i32, vp, i64, i32, f32, i32, f32, u16, u32, u8, f32, vp, i64, i64, C.POINTER(i64)]),
+    "urh_segment_shard_pass": (i32, [vp, vp, i32, i64, f32, vp]),
+    "urh_segments_from_runs": (i32, [vp, vp, i64, i32, i32, i64, i64, vp, i64, C.POINTER(i64)]),
+    "urh_fetch_candidates": (i32, [vp, vp, vp, i64]),
     "urh_pulses_from_table": (i32, [vp, vp, vp, i64, i64, u16, i32, u32, i32, C.POINTER(i64)]),
     "urh_costas_halo_samples": (i32, []),
     "urh_costas_shard_speculate": (i32, [vp, vp, i32, i64, i32, f32, i32, f32, vp]),
@@ -131,6 +134,7 @@ SIGNATURES = {
     "urh_nccl_allreduce_i64": (i32, [vp, vp, i64, i32]),
     "urh_nccl_allgather": (i32, [vp, vp, vp, szt]),
     "urh_nccl_gatherv": (i32, [vp, vp, vp, vp, i32]),
+    "urh_nccl_sendrecv": (i32, [vp, vp, szt, i32, vp, szt, i32]),
     "urh_set_profiling": (i32, [vp, i32]),
     "urh_last_dense_ms": (i32, [vp, C.POINTER(f32)]),
     "urh_costas_shard_hypotheses": (i32, [vp, vp, C.POINTER(i32)]),
@@ -138,6 +142,8 @@ SIGNATURES = {
     "urh_costas_stats": (i32, [vp, vp]),
     "urh_costas_last_redone": (i64, [vp]),
     "urh_selftest_packed_div": (i32, [vp, C.c_uint64, i64, C.POINTER(i64), C.POINTER(i64)]),
+    "urh_modulate_stats": (i32, [vp, vp]),
+    "urh_synth_psk": (i32, [vp, vp, i64, i64, i32, i32, C.c_double, f32, f32, C.c_uint64, i64, i64, i64]),
     "urh_synth_fsk": (i32, [vp, vp, i64, i64, i32, vp, vp, C.c_double, f32, f32, C.c_uint64, i64, i64, i64, i64, i64]),
 }
 

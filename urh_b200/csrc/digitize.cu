@@ -644,6 +644,17 @@ extern "C" int urh_shard_candidates(urh_ctx* ctx, int carry_valid, int carry_cls
     return URH_OK;
 }
 
+// host copies of the candidate table urh_shard_candidates left on the device
+extern "C" int urh_fetch_candidates(urh_ctx* ctx, int64_t* h_pos, int16_t* h_cls, int64_t count) {
+    UrhShardState* S = shard_state(ctx);
+    if (count < 0 || count > S->cand.count) URH_FAIL(ctx, URH_ERR_INVALID, "fetch_candidates: count exceeds the table");
+    if (count == 0) return URH_OK;
+    URH_CUDA(ctx, cudaMemcpyAsync(h_pos, S->cand.pos, (size_t)count * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaMemcpyAsync(h_cls, S->cand.cls, (size_t)count * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return URH_OK;
+}
+
 // Step 3 (distributed finish): prev_cls = class of the last candidate of the preceding shards (the digitizer's
 // initial state on the first shard).  Returns the number of firings and the position of the last one (-1: none).
 extern "C" int urh_shard_fire(urh_ctx* ctx, int prev_cls, int64_t* fired, int64_t* last_fired_pos) {

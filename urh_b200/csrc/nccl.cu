@@ -136,20 +136,51 @@ extern "C" int urh_nccl_gatherv(urh_ctx* ctx, const void* d_send, void* d_recv, 
     URH_CHECK(need_comm(ctx));
     urh_ncclComm_t comm = (urh_ncclComm_t)ctx->nccl_comm;
     URH_NCCL(ctx, g_nccl.GroupStart());
+    urh_ncclResult_t bad = 0;
+    cudaError_t cbad = cudaSuccess;
     if (ctx->nccl_rank == root) {
         int64_t off = 0;
         for (int r = 0; r < ctx->nccl_world; r++) {
             if (r == root) {
-                if (h_bytes[r] > 0) cudaMemcpyAsync((char*)d_recv + off, d_send, (size_t)h_bytes[r], cudaMemcpyDeviceToDevice, ctx->stream);
+                if (h_bytes[r] > 0) {
+                    const cudaError_t e = cudaMemcpyAsync((char*)d_recv + off, d_send, (size_t)h_bytes[r], cudaMemcpyDeviceToDevice, ctx->stream);
+                    if (e != cudaSuccess) cbad = e;
+                }
             } else if (h_bytes[r] > 0) {
-                g_nccl.Recv((char*)d_recv + off, (size_t)h_bytes[r], URH_NCCL_UINT8, r, comm, ctx->stream);
+                const urh_ncclResult_t e = g_nccl.Recv((char*)d_recv + off, (size_t)h_bytes[r], URH_NCCL_UINT8, r, comm, ctx->stream);
+                if (e != 0) bad = e;
             }
             off += h_bytes[r];
         }
     } else if (h_bytes[ctx->nccl_rank] > 0) {
-        g_nccl.Send(d_send, (size_t)h_bytes[ctx->nccl_rank], URH_NCCL_UINT8, root, comm, ctx->stream);
+        bad = g_nccl.Send(d_send, (size_t)h_bytes[ctx->nccl_rank], URH_NCCL_UINT8, root, comm, ctx->stream);
     }
-    URH_NCCL(ctx, g_nccl.GroupEnd());
+    const urh_ncclResult_t ge = g_nccl.GroupEnd();   // always close the group, then report the first failure
+    if (cbad != cudaSuccess) URH_FAIL(ctx, URH_ERR_CUDA, "gatherv: local copy failed: %s", cudaGetErrorString(cbad));
+    if (bad != 0) URH_FAIL(ctx, URH_ERR_CUDA, "gatherv: ncclSend/ncclRecv failed: %s", g_nccl.GetErrorString(bad));
+    URH_NCCL(ctx, ge);
+    return URH_OK;
+}
+
+// Grouped point-to-point exchange: send `send_bytes` to `send_peer` and receive `recv_bytes` from `recv_peer` (a peer < 0 or zero
+// bytes skips that half).  Used to hand a message that straddles a shard edge to the rank that owns its start.
+extern "C" int urh_nccl_sendrecv(urh_ctx* ctx, const void* d_send, size_t send_bytes, int send_peer, void* d_recv, size_t recv_bytes,
+                                 int recv_peer) {
+    URH_CHECK(need_comm(ctx));
+    urh_ncclComm_t comm = (urh_ncclComm_t)ctx->nccl_comm;
+    URH_NCCL(ctx, g_nccl.GroupStart());
+    urh_ncclResult_t bad = 0;
+    if (send_peer >= 0 && send_bytes > 0) {
+        const urh_ncclResult_t e = g_nccl.Send(d_send, send_bytes, URH_NCCL_UINT8, send_peer, comm, ctx->stream);
+        if (e != 0) bad = e;
+    }
+    if (recv_peer >= 0 && recv_bytes > 0) {
+        const urh_ncclResult_t e = g_nccl.Recv(d_recv, recv_bytes, URH_NCCL_UINT8, recv_peer, comm, ctx->stream);
+        if (e != 0) bad = e;
+    }
+    const urh_ncclResult_t ge = g_nccl.GroupEnd();
+    if (bad != 0) URH_FAIL(ctx, URH_ERR_CUDA, "sendrecv: ncclSend/ncclRecv failed: %s", g_nccl.GetErrorString(bad));
+    URH_NCCL(ctx, ge);
     return URH_OK;
 }
 

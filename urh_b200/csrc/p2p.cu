@@ -78,7 +78,8 @@ extern "C" int urh_p2p_open(urh_ctx* ctx, const char* handles, int rank, int wor
     if (!ctx->p2p_hout) URH_CUDA(ctx, cudaHostAlloc(&ctx->p2p_hout, (P2P_MAXW * P2P_WORDS + 8) * sizeof(unsigned long long), cudaHostAllocMapped));
     ctx->p2p_rank = rank;
     ctx->p2p_world = world;
-    ctx->p2p_seq = 0;
+    // p2p_seq is NOT reset: sequence numbers stay monotonic per context, so slots left over from an earlier session (or from a
+    // timed-out exchange) can never satisfy a later wait.  All ranks open together (dist.init_p2p), so their counters stay equal.
     return URH_OK;
 }
 
@@ -109,7 +110,11 @@ extern "C" int urh_p2p_allgather_host(urh_ctx* ctx, const void* h_send, void* h_
     URH_CUDA(ctx, cudaHostGetDevicePointer((void**)&d_hout, hout, 0));
     URH_LAUNCH(ctx, k_p2p_allgather, 1, 32, 0, a, d_hout);
     URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (hout[P2P_MAXW * P2P_WORDS]) URH_FAIL(ctx, URH_ERR_CUDA, "p2p all-gather timed out waiting for a peer (exchange %llu)", a.seq);
+    if (hout[P2P_MAXW * P2P_WORDS]) {
+        // the ranks may now disagree about the sequence: the mailboxes are unusable until re-opened; the caller falls back to NCCL
+        urh_p2p_close(ctx);
+        URH_FAIL(ctx, URH_ERR_CUDA, "p2p all-gather timed out waiting for a peer (exchange %llu); p2p closed", a.seq);
+    }
     for (int r = 0; r < ctx->p2p_world; r++) memcpy((char*)h_recv + (size_t)r * bytes_per_rank, hout + r * P2P_WORDS, bytes_per_rank);
     return URH_OK;
 }

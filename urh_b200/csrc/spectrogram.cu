@@ -84,7 +84,7 @@ __global__ void k_fft_twiddles(int W, double2* __restrict__ tw) {
 }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-    return make_double2(__dsub_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)), __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
 
 // MODE 0: out = complex128 [F][W] = X / W;  MODE 1: out = float32 [F][W] dB map (fftshift + fliplr + complex64 cast + 10 log10f)
@@ -145,17 +145,17 @@ __global__ void __launch_bounds__(256) k_stft_fused(const float2* __restrict__ x
         double2* t = a; a = b; b = t;
         ns <<= 2;
     }
-    const double dW = (double)W;
+    const double inv = 1.0 / (double)W;   // W is a power of two: multiplying by 1/W IS the division by W, bit for bit
     if (MODE == 0) {
         double2* out = (double2*)out_ + f * W;
-        for (int w = threadIdx.x; w < W; w += blockDim.x) out[w] = make_double2(a[w].x / dW, a[w].y / dW);
+        for (int w = threadIdx.x; w < W; w += blockDim.x) out[w] = make_double2(a[w].x * inv, a[w].y * inv);
     } else {
         float* out = (float*)out_ + f * W;
         const int shift = (W + 1) / 2;
         for (int j = threadIdx.x; j < W; j += blockDim.x) {
             const int src = ((W - 1 - j) + shift) & (W - 1);   // fliplr, then fftshift
             const double2 v = a[src];
-            const float re = (float)(v.x / dW), im = (float)(v.y / dW);   // complex128 / W, then astype(complex64)
+            const float re = (float)(v.x * inv), im = (float)(v.y * inv);   // complex128 / W, then astype(complex64)
             out[j] = __fmul_rn(10.0f, log10f(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im))));
         }
     }

@@ -189,6 +189,81 @@ static int run_table(urh_ctx* ctx, const T* d_x, int64_t n, float thr, int tol, 
     return URH_OK;
 }
 
+// The two-state machine of segment_messages_from_magnitudes over the run table (host; the runs of >= 10 samples are few):
+// h_pos / h_cls = candidates of tolerance 9 (index of the 10th consecutive sample of a run, its class 0 = below / 1 = above the
+// noise threshold), first_above = class of sample 0, (last_cls, last_len) = the run that ends the capture.  Pure host code, so the
+// sharded path (urh_b200/dist.py: candidates of all shards concatenated) shares it with urh_segment_messages.
+extern "C" int urh_segments_from_runs(const int64_t* h_pos, const int16_t* h_cls, int64_t count, int first_above, int last_cls,
+                                      int64_t last_len, int64_t n, int64_t* h_segments, int64_t cap, int64_t* k) {
+    int state = first_above ? 1 : 0;
+    int64_t start = 0, m = 0;
+    for (int64_t j = 0; j < count; j++) {
+        if (h_cls[j] == state) continue;
+        const int64_t p = h_pos[j];  // index of the 10th consecutive sample of the opposite class
+        if (state == 1) {
+            if (m < cap) { h_segments[2 * m] = start; h_segments[2 * m + 1] = p - 10; }
+            m++;
+            state = 0;
+        } else {
+            start = p - 10;
+            state = 1;
+        }
+    }
+    if (state == 1) {
+        const int64_t conseq_below = (last_cls == 0) ? last_len : 0;
+        if (start < n - conseq_below) {
+            if (m < cap) { h_segments[2 * m] = start; h_segments[2 * m + 1] = n - conseq_below; }
+            m++;
+        }
+    }
+    *k = m;
+    return URH_OK;
+}
+
+// One shard of a capture whose magnitudes are spread over the ranks: the dense pass (class = above the threshold, tolerance 9)
+// leaves the tile table for urh_shard_candidates (carry of the preceding shards, global positions).
+// h_summary = {last_cls, last_len, whole, class of the shard's first sample}.
+extern "C" int urh_segment_shard_pass(urh_ctx* ctx, const void* d_mags, int is_f64, int64_t n, float noise_threshold, int64_t* h_summary) {
+    if (n <= 0) URH_FAIL(ctx, URH_ERR_INVALID, "empty shard");
+    urh_arena_reset(ctx);
+    UrhClassify cls;
+    memset(&cls, 0, sizeof(cls));
+    cls.noise_value = 0.0f;
+    cls.order = 2;
+    cls.thr[0] = noise_threshold;
+    const int tol = 9;
+    const int64_t ntiles = urh_div_up(n, URH_TILE);
+    const int cap = URH_TILE / (tol + 1) + 2;
+    UrhTileSummary* tiles;
+    uint32_t* staging;
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles, &tiles));
+    URH_CHECK(urh_arena(ctx, (size_t)ntiles * cap, &staging));
+    const unsigned grid = (unsigned)urh_div_up(ntiles, URH_WARPS_PER_BLOCK);
+    double f0 = 0.0;
+    if (is_f64) {
+        const int vec_in = (((uintptr_t)d_mags % 16) == 0) ? 1 : 0;
+        URH_LAUNCH(ctx, (k_dense_f32<SrcAbove, double>), grid, URH_WARPS_PER_BLOCK * 32, 0, (const double*)d_mags, n, vec_in, cls, tol, tiles,
+                   staging, cap, (int16_t*)nullptr, 0);
+        URH_CUDA(ctx, cudaMemcpyAsync(&f0, d_mags, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        const int vec_in = (((uintptr_t)d_mags % 8) == 0) ? 1 : 0;
+        URH_LAUNCH(ctx, (k_dense_f32<SrcAbove, float>), grid, URH_WARPS_PER_BLOCK * 32, 0, (const float*)d_mags, n, vec_in, cls, tol, tiles,
+                   staging, cap, (int16_t*)nullptr, 0);
+        float f32 = 0.f;
+        URH_CUDA(ctx, cudaMemcpyAsync(&f32, d_mags, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        URH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        f0 = (double)f32;
+    }
+    ctx->shard_tiles = tiles;
+    ctx->shard_staging = staging;
+    ctx->shard_cap = cap;
+    ctx->shard_n = n;
+    ctx->shard_tol = tol;
+    URH_CHECK(urh_shard_run_total(ctx, n, tiles, h_summary));   // synchronises
+    h_summary[3] = (is_f64 ? (f0 > (double)noise_threshold) : ((float)f0 > noise_threshold)) ? 1 : 0;
+    return URH_OK;
+}
+
 // segment_messages_from_magnitudes (auto_interpretation.pyx:55-111).  d_mags float32 (is_f64=0) or float64.
 // h_segments receives (start, end) pairs, capacity `cap` pairs; *k = number of messages (may exceed cap: call again).
 extern "C" int urh_segment_messages(urh_ctx* ctx, const void* d_mags, int is_f64, int64_t n, float noise_threshold,
@@ -210,32 +285,10 @@ extern "C" int urh_segment_messages(urh_ctx* ctx, const void* d_mags, int is_f64
         URH_CHECK((run_table<SrcAbove, float>(ctx, (const float*)d_mags, n, noise_threshold, 9, &pos, &cl, &count, last)));
         first = (f0 > noise_threshold) ? 1.f : 0.f;
     }
-    // host tail: the two-state machine over the (few) runs of >= 10 samples
-    int state = first > 0.f ? 1 : 0;
-    int64_t start = 0, m = 0;
-    for (int64_t j = 0; j < count; j++) {
-        if (cl[j] == state) continue;
-        const int64_t p = pos[j];  // index of the 10th consecutive sample of the opposite class
-        if (state == 1) {
-            if (m < cap) { h_segments[2 * m] = start; h_segments[2 * m + 1] = p - 10; }
-            m++;
-            state = 0;
-        } else {
-            start = p - 10;
-            state = 1;
-        }
-    }
-    if (state == 1) {
-        const int64_t conseq_below = (last[0] == 0) ? last[1] : 0;
-        if (start < n - conseq_below) {
-            if (m < cap) { h_segments[2 * m] = start; h_segments[2 * m + 1] = n - conseq_below; }
-            m++;
-        }
-    }
+    const int rc = urh_segments_from_runs(pos, cl, count, first > 0.f ? 1 : 0, (int)last[0], last[1], n, h_segments, cap, k);
     free(pos);
     free(cl);
-    *k = m;
-    return URH_OK;
+    return rc;
 }
 
 // get_plateau_lengths (auto_interpretation.pyx:179-208): h_out capacity `cap`; *k = number of plateaus.

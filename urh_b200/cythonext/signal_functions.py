@@ -254,20 +254,22 @@ def modulate_batch(messages, samples_per_symbol, modulation_type, parameters, bi
         np.cumsum(int(per // bits_per_symbol) * int(samples_per_symbol) + pauses, out=out_off[1:])
         msgs = None
     else:
+        # ragged batch: per-message Python work only where it is unavoidable (lists -> arrays, the OQPSK bit shuffle);
+        # lengths and offsets are vectorised
         msgs = []
         for bits in messages:
-            b = np.ascontiguousarray(np.asarray(bits, dtype=np.uint8))
+            b = bits if (isinstance(bits, np.ndarray) and bits.dtype == np.uint8 and bits.ndim == 1) else \
+                np.ascontiguousarray(np.asarray(bits, dtype=np.uint8))
             if mod == "oqpsk" and len(b):
                 b = np.ascontiguousarray(get_oqpsk_bits(b)[: len(b)])  # only the first len(bits) shuffled bits are used
             msgs.append(b)
         nmsg = len(msgs)
-        pauses = [int(p) for p in (pauses if hasattr(pauses, "__len__") else [pauses] * nmsg)]
+        pauses = np.asarray(pauses if hasattr(pauses, "__len__") else [pauses] * nmsg, dtype=np.int64)
+        lens = np.fromiter((len(b) for b in msgs), dtype=np.int64, count=nmsg)
         bit_off = np.zeros(nmsg + 1, dtype=np.int64)
+        np.cumsum(lens, out=bit_off[1:])
         out_off = np.zeros(nmsg + 1, dtype=np.int64)
-        for m, b in enumerate(msgs):
-            bit_off[m + 1] = bit_off[m] + len(b)
-            nsym = int(len(b) // bits_per_symbol)
-            out_off[m + 1] = out_off[m] + nsym * int(samples_per_symbol) + pauses[m]
+        np.cumsum((lens // int(bits_per_symbol)) * int(samples_per_symbol) + pauses, out=out_off[1:])
     total = int(out_off[-1])
     params = np.ascontiguousarray(np.asarray(parameters, dtype=np.float32))
     d_out = DeviceArray(ctx, (total, 2), dtype)

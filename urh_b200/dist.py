@@ -471,3 +471,171 @@ def detect_noise_level_sharded(ctx, hx, sb: ShardBuffer, global_offset, n_total)
     ctx.check(ctx.lib.urh_nccl_allreduce_f64(ctx.handle, C.c_void_p(d_s.ptr), nchunks, 0))
     ctx.check(ctx.lib.urh_nccl_allreduce_f64(ctx.handle, C.c_void_p(d_m.ptr), nchunks, 1))
     return AI._noise_from_chunk_stats(n_total, chunksize, d_s.get(), d_m.get(), np.float64)
+
+
+# ---- AutoInterpretation.estimate over a sharded capture (BASELINE configs[4]) ------------------------------------------------------
+def segment_messages_sharded(ctx, hx, d_mag, global_offset, n_total, noise_threshold):
+    """segment_messages_from_magnitudes (auto_interpretation.pyx:55-111) of a capture whose magnitudes are spread over the ranks:
+    every rank runs the dense pass over its shard; the closing-run summaries are folded (``fold_carry``) so that runs crossing a
+    shard edge count their samples on both sides; the run tables (a few entries per message) are concatenated in rank order and
+    every rank runs the reference's two-state machine on them.  Returns the same list of (start, end) on every rank."""
+    lib = ctx.lib
+    n_local = len(d_mag)
+    summary = (C.c_int64 * 4)()
+    ctx.check(lib.urh_segment_shard_pass(ctx.handle, C.c_void_p(d_mag.ptr), int(d_mag.dtype == np.float64), n_local,
+                                         float(noise_threshold), summary))
+    every = hx.allgather((int(summary[0]), int(summary[1]), int(summary[2]), int(summary[3])))
+    carries = fold_carry([(c, l, w) for c, l, w, _ in every])
+    carry = carries[hx.rank]
+    count = C.c_int64(0)
+    ctx.check(lib.urh_shard_candidates(ctx.handle, int(carry is not None), carry[0] if carry else 0, carry[1] if carry else 0,
+                                       int(global_offset), C.byref(count), None, None, None))
+    pos = np.empty(count.value, dtype=np.int64)
+    cls = np.empty(count.value, dtype=np.int16)
+    if count.value:
+        ctx.check(lib.urh_fetch_candidates(ctx.handle, pos.ctypes.data_as(C.c_void_p), cls.ctypes.data_as(C.c_void_p), count.value))
+    tables = hx.allgather((pos, cls))
+    pos_all = np.ascontiguousarray(np.concatenate([t[0] for t in tables]))
+    cls_all = np.ascontiguousarray(np.concatenate([t[1] for t in tables]))
+    # the run that ends the capture: fold every shard's closing run
+    last_cls, last_len = None, 0
+    for c, l, w, _ in every:
+        if last_cls is not None and w and c == last_cls:
+            last_len += l
+        else:
+            last_cls, last_len = c, l
+    cap = max(16, len(pos_all) + 2)
+    seg = np.empty((cap, 2), dtype=np.int64)
+    k = C.c_int64(0)
+    ctx.check(lib.urh_segments_from_runs(pos_all.ctypes.data_as(C.c_void_p), cls_all.ctypes.data_as(C.c_void_p), len(pos_all), int(every[0][3]),
+                                         int(last_cls), int(last_len), int(n_total), seg.ctypes.data_as(C.c_void_p), cap, C.byref(k)))
+    return [(int(a), int(b)) for a, b in seg[: k.value]]
+
+
+def fetch_range(ctx, rank, bounds, d_local, g0, g1, owner):
+    """Collective: every rank calls it with the same (g0, g1, owner).  `d_local` is this rank's shard (1-D or (n, 2) DeviceArray) of
+    a capture cut at `bounds` [(start, end) per rank].  Returns on `owner` a DeviceArray with elements [g0, g1) of the capture
+    (its own part copied, the other parts received over NCCL); None elsewhere."""
+    lib = ctx.lib
+    item = d_local.nbytes // max(1, len(d_local))
+    out = None
+    if rank == owner:
+        shape = (g1 - g0,) + tuple(d_local.shape[1:])
+        out = DeviceArray(ctx, shape, d_local.dtype)
+    for q, (a, b) in enumerate(bounds):
+        lo, hi = max(a, g0), min(b, g1)
+        if lo >= hi:
+            continue
+        nbytes = (hi - lo) * item
+        if q == owner:
+            if rank == owner:
+                ctx.check(lib.urh_memcpy_d2d(ctx.handle, C.c_void_p(out.ptr + (lo - g0) * item), C.c_void_p(d_local.ptr + (lo - a) * item), nbytes))
+        elif rank == q:
+            ctx.check(lib.urh_nccl_sendrecv(ctx.handle, C.c_void_p(d_local.ptr + (lo - a) * item), nbytes, owner, None, 0, -1))
+        elif rank == owner:
+            ctx.check(lib.urh_nccl_sendrecv(ctx.handle, None, 0, -1, C.c_void_p(out.ptr + (lo - g0) * item), nbytes, q))
+    return out
+
+
+def estimate_sharded(ctx, hx, sb: ShardBuffer, bounds, n_total, noise=None, modulation=None):
+    """AutoInterpretation.estimate (AutoInterpretation.py:373-471) of ONE capture sharded by contiguous sample range: the same dict
+    on every rank, equal to the single-GPU / reference result.
+      noise       global end-aligned chunk statistics, NCCL all-reduce (detect_noise_level_sharded)
+      messages    sharded segmentation with run carry (segment_messages_sharded)
+      modulation  detect_modulation on the first 100 messages, each on the rank that owns its start
+      demod       ASK / FSK with the 1-sample halo; PSK with the speculative Costas loop over shards (afp_demod_psk_sharded)
+      parameters  detect_center / plateau lengths / tolerance / bit length per message on the owning rank (a message that
+                  straddles a shard edge is completed over NCCL), gathered and reduced exactly as the reference does."""
+    from .ainterpretation import AutoInterpretation as AI
+    from .cythonext import auto_interpretation as c_ai
+    from .cythonext import signal_functions as sf
+    from .cythonext import util
+
+    rank, world = hx.rank, hx.world
+    lo, hi = bounds[rank]
+    d_mag = util.get_magnitudes(sb.shard)
+    if noise is None:
+        noise = detect_noise_level_sharded(ctx, hx, sb, lo, n_total)
+    message_indices = segment_messages_sharded(ctx, hx, d_mag, lo, n_total, noise)
+    d_mag.free()
+
+    def owner_of(start):
+        for q, (a, b) in enumerate(bounds):
+            if a <= start < b:
+                return q
+        return world - 1
+
+    def message_slice(d_shard, start, end):
+        """[start, end) of the capture on the rank owning `start` (collective when the message leaves that rank's shard)"""
+        own = owner_of(start)
+        a, b = bounds[own]
+        if end <= b:
+            return (d_shard[start - a: end - a] if rank == own else None), own
+        return fetch_range(ctx, rank, bounds, d_shard, start, end, own), own
+
+    if modulation is None:
+        found_local = []
+        for idx, (start, end) in enumerate(message_indices[0:100]):
+            part, own = message_slice(sb.shard, start, end)
+            if rank == own:
+                from .signalprocessing.IQArray import IQArray
+                mod = AI.detect_modulation(IQArray(np.ascontiguousarray(part.get()), _owned=True).as_complex64())
+                if mod is not None:
+                    found_local.append((idx, mod))
+        found = sorted(x for part in hx.allgather(found_local) for x in part)
+        modulation = AI.most_common([m for _, m in found]) if found else None
+    if modulation is None:
+        return None
+    if modulation == "OOK":
+        message_indices = AI.merge_message_segments_for_ook(message_indices)
+    d_qad = DeviceArray(ctx, (hi - lo,), np.float32)
+    if modulation == "PSK":
+        afp_demod_psk_sharded(ctx, rank, world, sb, noise, 2, 0.1, d_qad)
+    else:
+        mt = "ASK" if modulation in ("OOK", "ASK") else "FSK"
+        kept = C.c_int64(0)
+        ctx.check(ctx.lib.urh_afp_demod_tiles(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, float(noise),
+                                              _lib.demod_mod_code(mt), C.c_void_p(d_qad.ptr), int(rank > 0), C.byref(kept)))
+    local = []   # (message index, center, bit_length or None, tolerance or None)
+    for idx, (start, end) in enumerate(message_indices):
+        msg, own = message_slice(d_qad, int(start), int(end))
+        if rank != own:
+            continue
+        center = AI.detect_center(msg)
+        if center is None:
+            continue
+        plateau_lengths = c_ai.get_plateau_lengths(msg, center, percentage=25)
+        tolerance = AI.estimate_tolerance_from_plateau_lengths(plateau_lengths)
+        tol_entry = None
+        if tolerance is None:
+            tolerance = 0
+        else:
+            tol_entry = tolerance
+        merged = AI.merge_plateau_lengths(plateau_lengths, tolerance=tolerance)
+        bit_entry = None
+        if len(merged) >= 2:
+            bit_length = AI.get_bit_length_from_plateau_lengths(merged)
+            if bit_length > tolerance + 1:
+                bit_entry = (float(center), bit_length)
+        local.append((idx, tol_entry, bit_entry))
+    rows = sorted(x for part in hx.allgather(local) for x in part)
+    tolerances = [t for _, t, _ in rows if t is not None]
+    centers = [b[0] for _, _, b in rows if b is not None]
+    bit_lengths = [b[1] for _, _, b in rows if b is not None]
+    if modulation in ("OOK", "ASK"):
+        center = AI.min_without_outliers(np.array(centers), z=2)
+        if center is None:
+            return None
+    elif len(centers) > 0:
+        center = np.mean(centers)
+    else:
+        return None
+    bit_length = AI.get_most_frequent_value(bit_lengths)
+    if bit_length is None:
+        return None
+    try:
+        tolerance = np.percentile(tolerances, 50)
+    except IndexError:
+        tolerance = max(1, int(0.05 * bit_length))
+    return {"modulation_type": "ASK" if modulation == "OOK" else modulation, "bit_length": bit_length, "center": center,
+            "tolerance": int(tolerance), "noise": noise}
