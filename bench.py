@@ -507,11 +507,14 @@ def main():
                 return udist.demod_digitize_distributed(ctx, rank, world, sb2, offset, n_total, NOISE_MAG, "FSK", CENTER, TOL, SPS)
         else:
             d_e2e = DeviceArray(ctx, (n, 2), np.float32)
+            rows_pinned = PinnedArray((n // 64 + 1024, 2), np.int64, ctx)   # pinned: the pulse table comes back as one DMA
 
             def step_e2e():
-                d_e2e.set_async(host.array)
                 if args.center == "detect":
-                    return sf.demod_center_digitize(d_e2e, NOISE_MAG, "FSK", TOL, SPS)[1]
+                    # host IQ in, host pulse table out: the upload is chunked on the copy stream and every chunk is demodulated as
+                    # soon as it has landed (urh_demod_center_digitize_host)
+                    return sf.demod_center_digitize(host.array, NOISE_MAG, "FSK", TOL, SPS, scratch=d_e2e, out=d_qad, rows_out=rows_pinned.array)[1]
+                d_e2e.set_async(host.array)
                 qad, rows = sf.demod_digitize(d_e2e, NOISE_MAG, "FSK", CENTER, TOL, SPS, return_qad=False)
                 return rows
 

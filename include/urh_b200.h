@@ -143,7 +143,7 @@ int urh_modulate_batch(urh_ctx* ctx, const uint8_t* d_bits, const int64_t* h_bit
                        uint32_t samples_per_symbol, int mod_type, const float* h_params, int nparams, int bits_per_symbol,
                        float carrier_amplitude, float carrier_frequency, float carrier_phase, float sample_rate,
                        uint32_t start, int out_dtype, const float* h_gauss_fir, int gauss_len, void* d_out);
-/* diagnostics: 32-sample blocks of the GFSK phase recurrence folded as an integer prefix sum / in order since the last call */
+/* diagnostics: steps of the GFSK phase recurrence taken through an integer prefix sum / one by one since the last call */
 int urh_modulate_stats(urh_ctx* ctx, int64_t* h_out2);
 
 /* ---- filters (filter.cu) ----------------------------------------------------------------------------------
@@ -193,6 +193,11 @@ int urh_shard_rows(urh_ctx* ctx, int64_t n_total, uint16_t tolerance, int mod_ty
 int urh_demod_center_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, float noise_mag, int mod_type,
                               uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size, float* d_qad_out,
                               double* center, int* center_state, int64_t* k);
+/* the same step fed from (pinned) HOST memory: chunked upload on the copy stream overlapped with the demodulation of the chunks
+ * that have landed (IQArray.from_file / Signal capture formats into device memory); chunk_samples <= 0: 2^24 */
+int urh_demod_center_digitize_host(urh_ctx* ctx, const void* h_iq, int dtype, int64_t n, float noise_mag, int mod_type,
+                                   uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size, int64_t chunk_samples,
+                                   void* d_iq_scratch, float* d_qad_out, double* center, int* center_state, int64_t* k);
 int urh_shard_demod_center_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int has_halo, float noise_mag,
                                     int mod_type, uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size,
                                     float* d_qad_out, int64_t global_offset, int64_t n_total, double* center,

@@ -126,3 +126,29 @@ def test_launch_count_of_the_step(sf):
     before = ctx.launch_count()
     sf.demod_center_digitize(iq, 0.05, "FSK", 5, 100)
     assert ctx.launch_count() - before <= 20
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.int16, np.int8])
+@pytest.mark.parametrize("chunk", [2048, 100_000, 1 << 24])
+def test_streamed_host_input_equals_resident(sf, dtype, chunk):
+    """urh_demod_center_digitize_host (chunked upload on the copy stream, each chunk demodulated as it lands) == the resident call"""
+    from urh_b200 import _lib
+    from urh_b200.device import PinnedArray, to_device
+
+    ctx = _lib.default_context()
+    n = 1_000_003
+    iq = synth_fsk(n, seed=5, gap_every=70_000, dtype=dtype)
+    noise = {np.float32: 0.05, np.int16: 1000.0, np.int8: 5.0}[dtype]
+    pinned = PinnedArray(iq.shape, iq.dtype, ctx)
+    pinned.array[...] = iq
+    rows_buf = PinnedArray((n // 8 + 1024, 2), np.int64, ctx)
+    c_host, r_host, q_host = sf.demod_center_digitize(pinned.array, noise, "FSK", 5, 100, return_qad=True, chunk_samples=chunk,
+                                                      rows_out=rows_buf.array)
+    c_dev, r_dev, q_dev = sf.demod_center_digitize(to_device(iq, ctx), noise, "FSK", 5, 100, return_qad=True)
+    assert bits_equal(q_host, q_dev.get()) == 0
+    assert c_host == c_dev
+    assert np.array_equal(r_host, r_dev)
+    assert r_host.base is not None   # a view of the caller's pinned buffer, no extra copy
+    r_host = None
+    pinned.free()
+    rows_buf.free()

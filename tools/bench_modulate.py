@@ -62,7 +62,7 @@ def main():
         print(json.dumps({"path": "modulate_batch %s %d x %d bits x %d sps + %d pause" % (mod, args.nmsg, args.bits, args.sps, args.pause),
                           "samples": total, "wall_ms": wall, "stream_ms": dev,
                           "GS_per_s_wall": total / wall / 1e6, "GS_per_s_stream": total / dev / 1e6,
-                          "write_GBps_stream": 8 * total / dev / 1e6, "gfsk_phase_blocks_prefix_sum_vs_in_order": [int(st[0]), int(st[1])], "frac_of_hbm_peak_stream": 8 * total / dev / 1e6 / peak}), flush=True)
+                          "write_GBps_stream": 8 * total / dev / 1e6, "gfsk_phase_steps_prefix_sum_vs_serial": [int(st[0]), int(st[1])], "frac_of_hbm_peak_stream": 8 * total / dev / 1e6 / peak}), flush=True)
 
 
 if __name__ == "__main__":

@@ -231,6 +231,12 @@ struct UrhRunTracker {
     // Same as feed() but with the boundary predicates supplied by the caller (fsk_fast.cuh derives them
     // without materialising class integers for the compare).
     __device__ __forceinline__ void walk(int it, uint32_t m0, uint32_t m1, int c0, int c1, int lane) {
+        // Few boundaries (a demodulated signal: one per symbol): walk them one by one, warp-uniformly.  Many boundaries (noise
+        // that is not gated: a class change at almost every sample): every lane settles its own two samples at once.
+        if (__popc(m0) + __popc(m1) > 4) {
+            walk_parallel(it, m0, m1, c0, c1, lane);
+            return;
+        }
         // merge the two boundary masks in sample order: sample 2l (mask m0) precedes sample 2l+1 (mask m1)
         while (m0 | m1) {
             const int l0 = m0 ? (__ffs(m0) - 1) : 64;
@@ -251,6 +257,57 @@ struct UrhRunTracker {
             run_start = p;
             run_cls = cls_p;
         }
+    }
+    // The same bookkeeping with O(1) work per 64-group, however many boundaries it holds.  A boundary at position p closes the
+    // run [q, p) that its PREDECESSOR boundary q opened (q = the nearest boundary below p in this group, else the carried
+    // run_start); the run's class is the class of sample p - 1.  The run emits a candidate at q + tol iff it is longer than tol
+    // and is not the tile's head run (the run that starts at the tile's first sample, handled by the tile stitching).
+    __device__ __forceinline__ void walk_parallel(int it, uint32_t m0, uint32_t m1, int c0, int c1, int lane) {
+        const uint32_t lt = (1u << lane) - 1u;
+        const int base = it * 64;
+        // class of the sample before each of my two samples
+        int cprev0 = __shfl_up_sync(URH_FULL_MASK, c1, 1);
+        if (lane == 0) cprev0 = run_cls;   // the carried run's class (== class of the previous group's last sample)
+        const int cprev1 = c0;
+        // nearest boundary below sample (l, 0): among m1 at lanes < l (position 2l'+1) and m0 at lanes < l (position 2l')
+        const uint32_t b1 = m1 & lt, b0 = m0 & lt;
+        int q0 = -1;   // relative to `base`; -1 = none in this group
+        if (b1) q0 = 2 * (31 - __clz(b1)) + 1;
+        if (b0) q0 = max(q0, 2 * (31 - __clz(b0)));
+        const bool has0 = (m0 >> lane) & 1u, has1 = (m1 >> lane) & 1u;
+        const int q1 = has0 ? 2 * lane : q0;
+        // absolute start of the run each of my boundaries closes, and whether that run is the head run
+        const bool carried_head = is_head;                 // the carried run (if any) is the head run
+        const int start0 = (q0 >= 0) ? base + q0 : run_start;
+        const int start1 = (q1 >= 0) ? base + q1 : run_start;
+        const int p0 = base + 2 * lane, p1 = p0 + 1;
+        // a run opened inside this group is the head run only if it starts at the tile's first sample (p == 0, it == 0)
+        const bool head0 = (q0 >= 0) ? (start0 == 0) : (carried_head || run_cls == -2);
+        const bool head1 = (q1 >= 0) ? (start1 == 0) : (carried_head || run_cls == -2);
+        const bool emit0 = has0 && !head0 && (p0 - start0 > tol);
+        const bool emit1 = has1 && !head1 && (p1 - start1 > tol);
+        const uint32_t e0 = __ballot_sync(URH_FULL_MASK, emit0), e1 = __ballot_sync(URH_FULL_MASK, emit1);
+        const int before = __popc(e0 & lt) + __popc(e1 & lt);
+        if (emit0) stage[ncand + before] = ((uint32_t)(start0 + tol) << 16) | (uint32_t)(cprev0 + 1);
+        if (emit1) stage[ncand + before + (emit0 ? 1 : 0)] = ((uint32_t)(start1 + tol) << 16) | (uint32_t)(cprev1 + 1);
+        ncand += __popc(e0) + __popc(e1);
+        // head run: it ends at the first boundary of the tile that is not the tile-opening one at p == 0
+        uint32_t f0 = m0, f1 = m1;
+        if (run_cls == -2) {   // the tile's first group: the forced boundary at p == 0 opens the head run
+            first_cls = __shfl_sync(URH_FULL_MASK, c0, 0);
+            f0 &= ~1u;
+        }
+        if (is_head && (f0 | f1)) {
+            const int l0 = f0 ? (__ffs(f0) - 1) : 64, l1 = f1 ? (__ffs(f1) - 1) : 64;
+            head_len = base + ((l0 <= l1) ? 2 * l0 : 2 * l1 + 1);
+            is_head = false;
+        }
+        // carry: the last boundary of the group opens the run that continues into the next group
+        const int h0 = m0 ? (31 - __clz(m0)) : -1, h1 = m1 ? (31 - __clz(m1)) : -1;
+        const bool last_is_1 = h1 >= h0;   // position 2*h1+1 > 2*h0 whenever h1 >= h0
+        const int hl = last_is_1 ? h1 : h0;
+        run_start = base + 2 * hl + (last_is_1 ? 1 : 0);
+        run_cls = __shfl_sync(URH_FULL_MASK, last_is_1 ? c1 : c0, hl);
     }
     __device__ __forceinline__ void finish(int tile_len, UrhTileSummary* out, int lane) {
         if (is_head) head_len = tile_len;

@@ -167,16 +167,22 @@ static float max_magnitude_for(int dtype) {
 
 static bool iq_vec_aligned(const void* p, int dtype) { return ((uintptr_t)p % (2 * (size_t)urh_iq_bytes(dtype))) == 0; }
 
+// tile_lo / tile_hi: restrict the pass to tiles [tile_lo, tile_hi) (chunked ingest: a chunk is demodulated as soon as its
+// upload has landed); tile_hi < 0 = all tiles.
 template <int DT, int MOD, bool DIG>
 static int launch_dense_iq_t(urh_ctx* ctx, const void* d_iq, int64_t n, const UrhDemodParams& dp, float* d_qad,
                              const UrhClassify& cls, int tol, UrhTileSummary* tiles, uint32_t* staging,
                              int stage_cap, int16_t* init_cls, int cls_of_zero, int has_halo = 0,
-                             UrhTileStats* tile_stats = nullptr) {
+                             UrhTileStats* tile_stats = nullptr, int64_t tile_lo = 0, int64_t tile_hi = -1) {
     const int64_t ntiles = urh_div_up(n, URH_TILE);
+    if (tile_hi < 0 || tile_hi > ntiles) tile_hi = ntiles;
     const int vec_in = iq_vec_aligned(d_iq, DT) ? 1 : 0;
     const int vec_out = (d_qad && ((uintptr_t)d_qad % 8) == 0) ? 1 : 0;
     const int threads = URH_WARPS_PER_BLOCK * 32;
-    auto generic = [&](int64_t begin, int64_t count) -> int {
+    auto generic = [&](int64_t begin, int64_t end) -> int {   // tiles [begin, end) clipped to the requested range
+        begin = begin < tile_lo ? tile_lo : begin;
+        end = end > tile_hi ? tile_hi : end;
+        const int64_t count = end - begin;
         if (count <= 0) return URH_OK;
         URH_LAUNCH(ctx, (k_dense_iq<DT, MOD, DIG>), (unsigned)urh_div_up(count, URH_WARPS_PER_BLOCK), threads, 0, d_iq, n, dp,
                    d_qad, vec_in, vec_out, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, begin, count, has_halo,
@@ -188,18 +194,21 @@ static int launch_dense_iq_t(urh_ctx* ctx, const void* d_iq, int64_t n, const Ur
     const bool fast = MOD == URH_MOD_FSK && vec_in && (!d_qad || vec_out) && (!DIG || cls.order == 2) && nfull > 1;
     URH_PROF_BEGIN(ctx);
     if (fast) {
-        const unsigned grid = (unsigned)urh_div_up(nfull - 1, URH_WARPS_PER_BLOCK);
-        if (tile_stats && d_qad && !DIG)
-            URH_LAUNCH(ctx, (k_fsk_fast<DT, false, true, true>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value,
-                       tol, tiles, staging, stage_cap, (int64_t)1, nfull - 1, tile_stats);
-        else if (d_qad)
-            URH_LAUNCH(ctx, (k_fsk_fast<DT, DIG, true, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
-                       tiles, staging, stage_cap, (int64_t)1, nfull - 1, nullptr);
-        else
-            URH_LAUNCH(ctx, (k_fsk_fast<DT, DIG, false, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
-                       tiles, staging, stage_cap, (int64_t)1, nfull - 1, nullptr);
+        const int64_t fb = tile_lo > 1 ? tile_lo : 1, fe = tile_hi < nfull ? tile_hi : nfull;
+        if (fe > fb) {
+            const unsigned grid = (unsigned)urh_div_up(fe - fb, URH_WARPS_PER_BLOCK);
+            if (tile_stats && d_qad && !DIG)
+                URH_LAUNCH(ctx, (k_fsk_fast<DT, false, true, true>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value,
+                           tol, tiles, staging, stage_cap, fb, fe - fb, tile_stats);
+            else if (d_qad)
+                URH_LAUNCH(ctx, (k_fsk_fast<DT, DIG, true, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
+                           tiles, staging, stage_cap, fb, fe - fb, nullptr);
+            else
+                URH_LAUNCH(ctx, (k_fsk_fast<DT, DIG, false, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
+                           tiles, staging, stage_cap, fb, fe - fb, nullptr);
+        }
         URH_CHECK(generic(0, 1));
-        URH_CHECK(generic(nfull, ntiles - nfull));
+        URH_CHECK(generic(nfull, ntiles));
     } else {
         URH_CHECK(generic(0, ntiles));
     }
@@ -211,13 +220,13 @@ template <int MOD, bool DIG>
 static int launch_dense_iq_m(urh_ctx* ctx, int dtype, const void* d_iq, int64_t n, const UrhDemodParams& dp,
                              float* d_qad, const UrhClassify& cls, int tol, UrhTileSummary* tiles,
                              uint32_t* staging, int stage_cap, int16_t* init_cls, int cls_of_zero, int has_halo = 0,
-                             UrhTileStats* tile_stats = nullptr) {
+                             UrhTileStats* tile_stats = nullptr, int64_t tile_lo = 0, int64_t tile_hi = -1) {
     switch (dtype) {
-        case URH_DT_I8: return launch_dense_iq_t<URH_DT_I8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats);
-        case URH_DT_U8: return launch_dense_iq_t<URH_DT_U8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats);
-        case URH_DT_I16: return launch_dense_iq_t<URH_DT_I16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats);
-        case URH_DT_U16: return launch_dense_iq_t<URH_DT_U16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats);
-        case URH_DT_F32: return launch_dense_iq_t<URH_DT_F32, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats);
+        case URH_DT_I8: return launch_dense_iq_t<URH_DT_I8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats, tile_lo, tile_hi);
+        case URH_DT_U8: return launch_dense_iq_t<URH_DT_U8, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats, tile_lo, tile_hi);
+        case URH_DT_I16: return launch_dense_iq_t<URH_DT_I16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats, tile_lo, tile_hi);
+        case URH_DT_U16: return launch_dense_iq_t<URH_DT_U16, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats, tile_lo, tile_hi);
+        case URH_DT_F32: return launch_dense_iq_t<URH_DT_F32, MOD, DIG>(ctx, d_iq, n, dp, d_qad, cls, tol, tiles, staging, stage_cap, init_cls, cls_of_zero, has_halo, tile_stats, tile_lo, tile_hi);
         default: URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
     }
 }
@@ -530,7 +539,8 @@ extern "C" int urh_shard_digitize(urh_ctx* ctx, const void* d_iq, int dtype, con
 // caller finishes through the stepwise entry points (urh_center_window_stats / urh_center_histogram_tiles / urh_grab_pulse_lens).
 static int demod_center_digitize_impl(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int has_halo, float noise_mag, int mod_type,
                                       uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size, float* d_qad_out, bool sharded,
-                                      int64_t global_offset, int64_t n_total, double* center, int* center_state, int64_t* k) {
+                                      int64_t global_offset, int64_t n_total, double* center, int* center_state, int64_t* k,
+                                      const void* h_iq = nullptr, int64_t chunk_samples = 0) {
     if (!k || !center || !center_state) return URH_ERR_INVALID;
     *k = 0;
     *center = 0.0;
@@ -547,10 +557,26 @@ static int demod_center_digitize_impl(urh_ctx* ctx, const void* d_iq, int dtype,
     const int64_t ntiles = urh_div_up(n, URH_TILE);
     UrhTileStats* ts;
     URH_CHECK(urh_arena(ctx, (size_t)ntiles, &ts));
-    if (mod_type == URH_MOD_ASK)
-        URH_CHECK((launch_dense_iq_m<URH_MOD_ASK, false>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, 0, nullptr, nullptr, 0, nullptr, 0, has_halo, ts)));
-    else
-        URH_CHECK((launch_dense_iq_m<URH_MOD_FSK, false>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, 0, nullptr, nullptr, 0, nullptr, 0, has_halo, ts)));
+    // h_iq != NULL: the capture is in (pinned) host memory.  It is uploaded in chunks on the copy stream and every chunk is
+    // demodulated as soon as it has landed, so the demodulation pass hides behind the PCIe transfer.
+    const int64_t chunk_tiles = (h_iq && chunk_samples > 0) ? (chunk_samples >= URH_TILE ? chunk_samples / URH_TILE : 1) : ntiles;
+    const size_t sample_bytes = (size_t)urh_iq_bytes(dtype);
+    int chunk_no = 0;
+    for (int64_t t0 = 0; t0 < ntiles; t0 += chunk_tiles, chunk_no++) {
+        const int64_t t1 = (t0 + chunk_tiles < ntiles) ? t0 + chunk_tiles : ntiles;
+        if (h_iq) {
+            const int64_t s0 = t0 * URH_TILE, s1 = (t1 * URH_TILE < n) ? t1 * URH_TILE : n;
+            cudaEvent_t ev = ctx->ev_copy[chunk_no & 1];
+            URH_CUDA(ctx, cudaMemcpyAsync((char*)d_iq + (size_t)s0 * sample_bytes, (const char*)h_iq + (size_t)s0 * sample_bytes,
+                                          (size_t)(s1 - s0) * sample_bytes, cudaMemcpyHostToDevice, ctx->copy_stream[0]));
+            URH_CUDA(ctx, cudaEventRecord(ev, ctx->copy_stream[0]));
+            URH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
+        }
+        if (mod_type == URH_MOD_ASK)
+            URH_CHECK((launch_dense_iq_m<URH_MOD_ASK, false>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, 0, nullptr, nullptr, 0, nullptr, 0, has_halo, ts, t0, t1)));
+        else
+            URH_CHECK((launch_dense_iq_m<URH_MOD_FSK, false>(ctx, dtype, d_iq, n, dp, d_qad_out, cls, 0, nullptr, nullptr, 0, nullptr, 0, has_halo, ts, t0, t1)));
+    }
     CenterPlan* plan = nullptr;
     URH_CHECK(urh_center_chain(ctx, d_qad_out, n, ts, max_size, sharded ? ctx->nccl_rank : 0, sharded ? ctx->nccl_world : 1, &plan));
     const float* d_centerf;
@@ -597,6 +623,20 @@ extern "C" int urh_demod_center_digitize(urh_ctx* ctx, const void* d_iq, int dty
                                          double* center, int* center_state, int64_t* k) {
     return demod_center_digitize_impl(ctx, d_iq, dtype, n, 0, noise_mag, mod_type, tolerance, samples_per_symbol, max_size, d_qad_out, false,
                                       0, n, center, center_state, k);
+}
+
+// The same step fed from HOST memory (pinned for a truly asynchronous copy): the IQ samples are uploaded into d_iq_scratch in
+// chunks of `chunk_samples` on the copy stream while the compute stream demodulates the chunks that have landed (streaming
+// ingest).  chunk_samples <= 0: 2^24.  Works for every IQArray dtype (int8 / int16 captures move 4x / 2x fewer bytes).
+extern "C" int urh_demod_center_digitize_host(urh_ctx* ctx, const void* h_iq, int dtype, int64_t n, float noise_mag, int mod_type,
+                                              uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size, int64_t chunk_samples,
+                                              void* d_iq_scratch, float* d_qad_out, double* center, int* center_state, int64_t* k) {
+    if (!h_iq || !d_iq_scratch) return URH_ERR_INVALID;
+    // the copy stream must not run ahead of work already queued on the compute stream that still reads the scratch buffer
+    URH_CUDA(ctx, cudaEventRecord(ctx->ev_comp[0], ctx->stream));
+    URH_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream[0], ctx->ev_comp[0], 0));
+    return demod_center_digitize_impl(ctx, d_iq_scratch, dtype, n, 0, noise_mag, mod_type, tolerance, samples_per_symbol, max_size, d_qad_out,
+                                      false, 0, n, center, center_state, k, h_iq, chunk_samples > 0 ? chunk_samples : ((int64_t)1 << 24));
 }
 
 extern "C" int urh_shard_demod_center_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int has_halo, float noise_mag,

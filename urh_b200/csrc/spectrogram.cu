@@ -88,77 +88,108 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 }
 
 // MODE 0: out = complex128 [F][W] = X / W;  MODE 1: out = float32 [F][W] dB map (fftshift + fliplr + complex64 cast + 10 log10f)
-template <int MODE>
-__global__ void __launch_bounds__(256) k_stft_fused(const float2* __restrict__ x, int64_t n, int W, int log2w, int hop,
-                                                   const double* __restrict__ window, const double2* __restrict__ tw,
-                                                   int64_t nframes, void* __restrict__ out_) {
-    extern __shared__ double2 s_buf[];   // two W-element buffers
+// W = 2^LOG2W and the thread count are compile-time: every loop below is fully unrolled (the W / THREADS loads of a thread are
+// in flight together — the first version, with run-time W, was bound by the latency of one load after the other — and the index
+// arithmetic of the stages is shifts and masks).
+template <int LOG2W, int THREADS, int MODE>
+__global__ void __launch_bounds__(THREADS) k_stft_fused(const float2* __restrict__ x, int64_t n, int hop,
+                                                       const double* __restrict__ window, const double2* __restrict__ tw,
+                                                       int64_t nframes, void* __restrict__ out_) {
+    constexpr int W = 1 << LOG2W;
+    constexpr int PER = W / THREADS;          // elements per thread in the load / store phases
+    constexpr int BPT = (W / 4) / THREADS > 0 ? (W / 4) / THREADS : 1;   // radix-4 butterflies per thread and stage
+    extern __shared__ double2 s_buf[];        // two W-element buffers
     double2* a = s_buf;
     double2* b = s_buf + W;
     const int64_t f = blockIdx.x;
     const int64_t base = f * hop;
-    for (int w = threadIdx.x; w < W; w += blockDim.x) {
-        const int64_t i = base + w;
-        double2 v = make_double2(0.0, 0.0);
-        if (i < n) {
-            const float2 sm = x[i];
-            const double g = window[w];
-            v = make_double2((double)sm.x * g, (double)sm.y * g);
+    {
+        float2 sm[PER];
+        double g[PER];
+#pragma unroll
+        for (int r = 0; r < PER; r++) {
+            const int w = threadIdx.x + r * THREADS;
+            const int64_t i = base + w;
+            sm[r] = (i < n) ? x[i] : make_float2(0.0f, 0.0f);
+            g[r] = window[w];
         }
-        a[w] = v;
+#pragma unroll
+        for (int r = 0; r < PER; r++) a[threadIdx.x + r * THREADS] = make_double2((double)sm[r].x * g[r], (double)sm[r].y * g[r]);
     }
     __syncthreads();
-    int ns = 1;        // length of the sub-transforms finished so far
-    int done = 0;
-    if (log2w & 1) {   // one radix-2 stage first
-        for (int j = threadIdx.x; j < W / 2; j += blockDim.x) {
+    if (LOG2W & 1) {   // one radix-2 stage first
+#pragma unroll
+        for (int r = 0; r < (W / 2) / THREADS; r++) {
+            const int j = threadIdx.x + r * THREADS;
             const double2 u = a[j], v = a[j + W / 2];
             b[2 * j] = make_double2(u.x + v.x, u.y + v.y);
             b[2 * j + 1] = make_double2(u.x - v.x, u.y - v.y);
         }
         __syncthreads();
         double2* t = a; a = b; b = t;
-        ns = 2;
-        done = 1;
     }
-    for (; done < log2w; done += 2) {
-        const int quarter = W / 4;
-        const int tstep = W / (4 * ns);   // twiddle index step: exp(-2 pi i r k / (4 ns)) = tw[r * k * tstep]
-        for (int j = threadIdx.x; j < quarter; j += blockDim.x) {
-            const int k = j & (ns - 1);
-            double2 v0 = a[j], v1 = a[j + quarter], v2 = a[j + 2 * quarter], v3 = a[j + 3 * quarter];
-            if (k) {
-                v1 = cmul(v1, tw[k * tstep]);
-                v2 = cmul(v2, tw[2 * k * tstep]);
-                v3 = cmul(v3, tw[3 * k * tstep]);
+#pragma unroll
+    for (int st = 0; st < LOG2W / 2; st++) {
+        const int ns = 1 << (2 * st + (LOG2W & 1));   // length of the sub-transforms finished so far (compile-time after unrolling)
+        constexpr int quarter = W / 4;
+        const int tstep = W / (4 * ns);               // exp(-2 pi i r k / (4 ns)) = tw[r * k * tstep]
+#pragma unroll
+        for (int r = 0; r < BPT; r++) {
+            const int j = threadIdx.x + r * THREADS;
+            if (j < quarter) {
+                const int k = j & (ns - 1);
+                double2 v0 = a[j], v1 = a[j + quarter], v2 = a[j + 2 * quarter], v3 = a[j + 3 * quarter];
+                if (ns > 1) {
+                    v1 = cmul(v1, tw[k * tstep]);
+                    v2 = cmul(v2, tw[2 * k * tstep]);
+                    v3 = cmul(v3, tw[3 * k * tstep]);
+                }
+                // DFT of length 4 (forward: -i rotation)
+                const double2 s02 = make_double2(v0.x + v2.x, v0.y + v2.y), d02 = make_double2(v0.x - v2.x, v0.y - v2.y);
+                const double2 s13 = make_double2(v1.x + v3.x, v1.y + v3.y), d13 = make_double2(v1.x - v3.x, v1.y - v3.y);
+                const int j0 = ((j - k) << 2) + k;   // (j / ns) * 4 ns + k
+                b[j0] = make_double2(s02.x + s13.x, s02.y + s13.y);
+                b[j0 + ns] = make_double2(d02.x + d13.y, d02.y - d13.x);      // d02 - i d13
+                b[j0 + 2 * ns] = make_double2(s02.x - s13.x, s02.y - s13.y);
+                b[j0 + 3 * ns] = make_double2(d02.x - d13.y, d02.y + d13.x);  // d02 + i d13
             }
-            // DFT of length 4 (forward: -i rotation)
-            const double2 s02 = make_double2(v0.x + v2.x, v0.y + v2.y), d02 = make_double2(v0.x - v2.x, v0.y - v2.y);
-            const double2 s13 = make_double2(v1.x + v3.x, v1.y + v3.y), d13 = make_double2(v1.x - v3.x, v1.y - v3.y);
-            const int j0 = ((j - k) << 2) + k;   // (j / ns) * 4 ns + k
-            b[j0] = make_double2(s02.x + s13.x, s02.y + s13.y);
-            b[j0 + ns] = make_double2(d02.x + d13.y, d02.y - d13.x);      // d02 - i d13
-            b[j0 + 2 * ns] = make_double2(s02.x - s13.x, s02.y - s13.y);
-            b[j0 + 3 * ns] = make_double2(d02.x - d13.y, d02.y + d13.x);  // d02 + i d13
         }
         __syncthreads();
         double2* t = a; a = b; b = t;
-        ns <<= 2;
     }
     const double inv = 1.0 / (double)W;   // W is a power of two: multiplying by 1/W IS the division by W, bit for bit
     if (MODE == 0) {
         double2* out = (double2*)out_ + f * W;
-        for (int w = threadIdx.x; w < W; w += blockDim.x) out[w] = make_double2(a[w].x * inv, a[w].y * inv);
+#pragma unroll
+        for (int r = 0; r < PER; r++) {
+            const int w = threadIdx.x + r * THREADS;
+            out[w] = make_double2(a[w].x * inv, a[w].y * inv);
+        }
     } else {
         float* out = (float*)out_ + f * W;
-        const int shift = (W + 1) / 2;
-        for (int j = threadIdx.x; j < W; j += blockDim.x) {
+        constexpr int shift = (W + 1) / 2;
+#pragma unroll
+        for (int r = 0; r < PER; r++) {
+            const int j = threadIdx.x + r * THREADS;
             const int src = ((W - 1 - j) + shift) & (W - 1);   // fliplr, then fftshift
             const double2 v = a[src];
             const float re = (float)(v.x * inv), im = (float)(v.y * inv);   // complex128 / W, then astype(complex64)
             out[j] = __fmul_rn(10.0f, log10f(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im))));
         }
     }
+}
+
+template <int LOG2W, int MODE>
+static int stft_fused_launch(urh_ctx* ctx, const float* d_x, int64_t n, int hop, const double* d_window, const double2* tw,
+                             int64_t num_frames, void* d_out) {
+    constexpr int W = 1 << LOG2W;
+    constexpr int THREADS = (W / 4 >= 256) ? 256 : (W / 4 >= 32 ? W / 4 : 32);
+    const size_t smem = (size_t)2 * W * sizeof(double2);
+    if (smem > 48 * 1024)
+        URH_CUDA(ctx, cudaFuncSetAttribute(k_stft_fused<LOG2W, THREADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    URH_LAUNCH(ctx, (k_stft_fused<LOG2W, THREADS, MODE>), (unsigned)num_frames, THREADS, smem, (const float2*)d_x, n, hop, d_window, tw,
+               num_frames, d_out);
+    return URH_OK;
 }
 
 static int stft_fused(urh_ctx* ctx, const float* d_x, int64_t n, int W, int hop, const double* d_window, int64_t num_frames,
@@ -169,20 +200,17 @@ static int stft_fused(urh_ctx* ctx, const float* d_x, int64_t n, int W, int hop,
     double2* tw;
     URH_CHECK(urh_arena(ctx, (size_t)W, &tw));
     URH_LAUNCH(ctx, k_fft_twiddles, (unsigned)urh_div_up(W, 256), 256, 0, W, tw);
-    const size_t smem = (size_t)2 * W * sizeof(double2);
-    if (smem > 48 * 1024) {
-        URH_CUDA(ctx, cudaFuncSetAttribute(k_stft_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        URH_CUDA(ctx, cudaFuncSetAttribute(k_stft_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    const int threads = W / 4 >= 256 ? 256 : (W / 4 < 32 ? 32 : W / 4);
     // grid.x is limited to 2^31 - 1 frames: far beyond any capture that fits the device
-    if (mode == 0)
-        URH_LAUNCH(ctx, k_stft_fused<0>, (unsigned)num_frames, threads, smem, (const float2*)d_x, n, W, log2w, hop, d_window,
-                   (const double2*)tw, num_frames, d_out);
-    else
-        URH_LAUNCH(ctx, k_stft_fused<1>, (unsigned)num_frames, threads, smem, (const float2*)d_x, n, W, log2w, hop, d_window,
-                   (const double2*)tw, num_frames, d_out);
-    return URH_OK;
+#define STFT_CASE(L)                                                                                                          \
+    case L:                                                                                                                   \
+        return mode == 0 ? stft_fused_launch<L, 0>(ctx, d_x, n, hop, d_window, (const double2*)tw, num_frames, d_out)         \
+                         : stft_fused_launch<L, 1>(ctx, d_x, n, hop, d_window, (const double2*)tw, num_frames, d_out);
+    switch (log2w) {
+        STFT_CASE(7) STFT_CASE(8) STFT_CASE(9) STFT_CASE(10) STFT_CASE(11) STFT_CASE(12)
+        default: break;
+    }
+#undef STFT_CASE
+    URH_FAIL(ctx, URH_ERR_INVALID, "stft_fused: unsupported window size");
 }
 
 static int ensure_plan(urh_ctx* ctx, int W, int64_t batch) {
@@ -206,8 +234,8 @@ static int ensure_plan(urh_ctx* ctx, int W, int64_t batch) {
 static int stft_run(urh_ctx* ctx, const float* d_x, int64_t n, int W, int hop, const double* d_window, int64_t num_frames,
                     void* d_out, int mode) {
     if (W <= 0 || hop <= 0 || num_frames <= 0) URH_FAIL(ctx, URH_ERR_INVALID, "stft: bad window/hop/frames");
-    // power-of-two windows up to 4096 (128 KB of shared memory): the fused kernel; anything else: cuFFT with two kernels around it
-    if ((W & (W - 1)) == 0 && W >= 4 && W <= 4096 && num_frames < ((int64_t)1 << 31) && !getenv("URH_B200_STFT_CUFFT"))
+    // power-of-two windows 128 .. 4096 (128 KB of shared memory): the fused kernel; anything else: cuFFT with two kernels around it
+    if ((W & (W - 1)) == 0 && W >= 128 && W <= 4096 && num_frames < ((int64_t)1 << 31) && !getenv("URH_B200_STFT_CUFFT"))
         return stft_fused(ctx, d_x, n, W, hop, d_window, num_frames, d_out, mode);
     urh_arena_reset(ctx);
     const int64_t max_batch = max((int64_t)1, ((int64_t)512 << 20) / ((int64_t)W * 16));

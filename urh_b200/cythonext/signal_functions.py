@@ -58,8 +58,13 @@ def get_center_thresholds(center: float, spacing: float, modulation_order: int) 
     return out
 
 
-def _fetch_pulses(ctx, k: int) -> np.ndarray:
-    rows = np.empty((k, 2), dtype=np.int64)
+def _fetch_pulses(ctx, k: int, out=None) -> np.ndarray:
+    """the pulse table of the last digitizer call; ``out``: a caller-owned int64 buffer with room for k rows (pinned memory
+    makes the download a true DMA: PinnedArray((rows, 2), np.int64).array) — a view of its first k rows is returned"""
+    if out is not None and out.dtype == np.int64 and out.size >= 2 * k and out.flags.c_contiguous:
+        rows = out.reshape(-1)[: 2 * k].reshape(k, 2)
+    else:
+        rows = np.empty((k, 2), dtype=np.int64)
     if k:
         ctx.check(ctx.lib.urh_fetch_pulses(ctx.handle, rows.ctypes.data_as(C.c_void_p), k))
     return rows
@@ -125,7 +130,7 @@ def demod_digitize(samples, noise_mag: float, mod_type: str, center: float, tole
 
 def demod_center_digitize(samples, noise_mag: float, mod_type: str, tolerance: int, samples_per_symbol: int,
                           bits_per_symbol: int = 1, center_spacing: float = 0.1, max_size=None, return_qad: bool = False,
-                          stepwise: bool = False, out=None):
+                          stepwise: bool = False, out=None, rows_out=None, scratch=None, chunk_samples: int = 1 << 24):
     """afp_demod -> detect_center -> grab_pulse_lens for a capture whose center is not known yet (ASK/FSK): three passes
     over sample-rate data instead of the reference's five (demod + tile statistics, histogram of qad, digitize from qad).
     Binary symbols run as ONE library call (urh_demod_center_digitize): bin edges, histogram, peak pick and the pulse table
@@ -141,16 +146,25 @@ def demod_center_digitize(samples, noise_mag: float, mod_type: str, tolerance: i
         samples = _check_iq(samples)
         ctx = samples.ctx if on_device else _lib.default_context()
         n = len(samples)
-        d_iq = samples if on_device else to_device(samples, ctx)
         if qad is None:
             qad = DeviceArray(ctx, (n,), np.float32)
         center, state, k = C.c_double(0.0), C.c_int(0), C.c_int64(0)
-        ctx.check(ctx.lib.urh_demod_center_digitize(ctx.handle, C.c_void_p(d_iq.ptr), _lib.dtype_code(d_iq.dtype), n, float(noise_mag),
-                                                    code, int(tolerance), int(samples_per_symbol), -1 if max_size is None else int(max_size),
-                                                    C.c_void_p(qad.ptr), C.byref(center), C.byref(state), C.byref(k)))
+        if on_device:
+            d_iq = samples
+            ctx.check(ctx.lib.urh_demod_center_digitize(ctx.handle, C.c_void_p(d_iq.ptr), _lib.dtype_code(d_iq.dtype), n, float(noise_mag),
+                                                        code, int(tolerance), int(samples_per_symbol), -1 if max_size is None else int(max_size),
+                                                        C.c_void_p(qad.ptr), C.byref(center), C.byref(state), C.byref(k)))
+        else:
+            host = np.ascontiguousarray(samples)
+            d_iq = scratch if scratch is not None else DeviceArray(ctx, host.shape, host.dtype)
+            ctx.check(ctx.lib.urh_demod_center_digitize_host(ctx.handle, host.ctypes.data_as(C.c_void_p), _lib.dtype_code(host.dtype), n,
+                                                             float(noise_mag), code, int(tolerance), int(samples_per_symbol),
+                                                             -1 if max_size is None else int(max_size), int(chunk_samples), C.c_void_p(d_iq.ptr),
+                                                             C.c_void_p(qad.ptr), C.byref(center), C.byref(state), C.byref(k)))
+            samples = d_iq   # the capture is on the device now (the stepwise fallback below reuses it)
         if state.value != 2:
             c = float(center.value) if state.value == 1 else None
-            rows = _fetch_pulses(ctx, k.value) if c is not None else np.zeros((0, 2), dtype=np.int64)
+            rows = _fetch_pulses(ctx, k.value, rows_out) if c is not None else np.zeros((0, 2), dtype=np.int64)
             if return_qad:
                 return c, rows, (qad if on_device else qad.get())
             return c, rows
