@@ -164,6 +164,10 @@ int urh_stft(urh_ctx* ctx, const float* d_x, int64_t n, int window_size, int hop
              double* d_out);
 int urh_spectrogram_db(urh_ctx* ctx, const float* d_x, int64_t n, int window_size, int hop, const double* d_window,
                        int64_t num_frames, float* d_out);
+/* Spectrogram.apply_bgra_lookup (Spectrogram.py:192-206): d_out[cols][rows][4] = colormap[clip(int((entries - 1) * ((data.T - min) /
+ * (max - min))))], colormap = entries x 4 bytes (blue, green, red, alpha); normalize = 0: the data are indices already. */
+int urh_bgra_lookup(urh_ctx* ctx, const float* d_data, int64_t rows, int64_t cols, const uint8_t* d_colormap, int entries,
+                    float data_min, float data_max, int normalize, uint8_t* d_out);
 
 /* ---- sharded captures: one contiguous sample range per GPU (digitize.cu, nccl.cu) ----------
  * urh_shard_dense      every rank: demodulate + classify its shard (d_iq[-1] = halo sample when has_halo);

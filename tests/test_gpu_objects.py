@@ -381,3 +381,28 @@ def test_gfsk_is_as_close_to_the_float64_truth_as_the_reference(sp, oracle, nbit
     # the reference's own distance to the truth grows with the message (float32 phase random walk: 2e-4 at 96 bits x 50 sps,
     # 2.5e-2 at 1000 bits x 100 sps on this image's CPU); the two float32 results stay within twice that of each other
     assert np.abs(gpu - ref).max() <= 2.0 * np.abs(ref - truth).max() + 1e-5
+
+
+def test_fft_convolve_matches_reference_formula(sp):
+    """Filter.fft_convolve_1d: the reference's power-of-two FFT product in complex128 vs the GPU's direct double convolution
+    (complex64 result): 1e-5 of the signal scale, float64 input included; the len(h) <= 2 quirk (empty result) is reproduced"""
+    rng = np.random.default_rng(12)
+
+    def ref(x, h):
+        n = len(x) + len(h) - 1
+        n_opt = 1 << (n - 1).bit_length()
+        result = np.fft.ifft(np.fft.fft(x, n_opt) * np.fft.fft(h, n_opt), n_opt)[0:n]
+        too_much = (len(result) - len(x)) // 2
+        return result[too_much:-too_much]
+
+    for n, m, dt in ((5000, 101, np.complex64), (777, 33, np.complex128), (64, 3, np.complex128)):
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(dt)
+        h = (rng.standard_normal(m) + 1j * rng.standard_normal(m)) / m
+        got = sp.Filter.fft_convolve_1d(x, h)
+        want = ref(x, h)
+        assert got.shape == want.shape
+        scale = max(np.abs(want).max(), np.sqrt(np.mean(np.abs(want) ** 2)))
+        assert np.abs(got - want).max() <= 1e-5 * scale
+    for m in (1, 2):
+        x = rng.standard_normal(50).astype(np.complex64)
+        assert len(sp.Filter.fft_convolve_1d(x, np.ones(m, dtype=complex))) == len(ref(x, np.ones(m, dtype=complex))) == 0

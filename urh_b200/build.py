@@ -67,7 +67,11 @@ def build(force=False, verbose=False):
         return LIB
     if not os.path.isfile(NVCC):
         if os.path.isfile(LIB):
-            return LIB  # prebuilt library shipped to a box without nvcc
+            # prebuilt library shipped to a box without nvcc: usable only if it was built from THESE sources
+            import warnings
+            warnings.warn("urh_b200: nvcc not found and liburh_b200.so does not match the sources' digest (stale build?); "
+                          "_lib.load_library() checks every prototype, a missing symbol fails loudly")
+            return LIB
         raise RuntimeError("nvcc not found and no prebuilt liburh_b200.so")
     objs = []
     procs = []

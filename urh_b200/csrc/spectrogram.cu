@@ -9,6 +9,7 @@
 #include "common.cuh"
 
 #include <cufft.h>
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -263,4 +264,40 @@ extern "C" int urh_stft(urh_ctx* ctx, const float* d_x, int64_t n, int window_si
 extern "C" int urh_spectrogram_db(urh_ctx* ctx, const float* d_x, int64_t n, int window_size, int hop, const double* d_window,
                                   int64_t num_frames, float* d_out) {
     return stft_run(ctx, d_x, n, window_size, hop, d_window, num_frames, d_out, 1);
+}
+
+// ---- BGRA colormap look-up (Spectrogram.apply_bgra_lookup, Spectrogram.py:192-206) --------------------------------
+// out[c][r] = colormap[clip(int((L - 1) * ((data[r][c] - data_min) / (data_max - data_min))))]   (data.T: the image is transposed)
+// float32 arithmetic in numpy's order: subtract, divide, multiply, truncate toward zero (astype(int)), np.take(mode="clip").
+__global__ void k_bgra_lookup(const float* __restrict__ data, int64_t rows, int64_t cols, const uint32_t* __restrict__ colormap, int L,
+                              float data_min, float range, int normalize, uint32_t* __restrict__ out) {
+    __shared__ uint32_t s_map[1024];
+    const bool in_smem = L <= 1024;
+    if (in_smem)
+        for (int i = threadIdx.x; i < L; i += blockDim.x) s_map[i] = colormap[i];
+    __syncthreads();
+    const int64_t total = rows * cols;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float scale = (float)(L - 1);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int64_t c = idx / rows, r = idx - c * rows;   // output index (c, r) <- data[r][c]
+        float v = data[r * cols + c];
+        if (normalize) v = __fmul_rn(scale, __fdiv_rn(__fsub_rn(v, data_min), range));
+        // astype(int): truncation; NaN and out-of-range values become INT64_MIN in numpy, which mode="clip" maps to entry 0
+        long long k = (v == v && fabsf(v) < 9.0e18f) ? (long long)v : LLONG_MIN;
+        k = k < 0 ? 0 : (k > L - 1 ? L - 1 : k);
+        out[idx] = in_smem ? s_map[k] : colormap[k];
+    }
+}
+
+extern "C" int urh_bgra_lookup(urh_ctx* ctx, const float* d_data, int64_t rows, int64_t cols, const uint8_t* d_colormap, int entries,
+                               float data_min, float data_max, int normalize, uint8_t* d_out) {
+    if (rows <= 0 || cols <= 0) return URH_OK;
+    if (entries <= 0) URH_FAIL(ctx, URH_ERR_INVALID, "bgra_lookup: empty colormap");
+    // the reference forms (data_max - data_min) in Python floats; as a weak scalar it meets the float32 array as a float32
+    const float r32 = (float)((double)data_max - (double)data_min);
+    const unsigned grid = (unsigned)min(urh_div_up(rows * cols, 256), (int64_t)ctx->sm_count * 16);
+    URH_LAUNCH(ctx, k_bgra_lookup, grid, 256, 0, d_data, rows, cols, (const uint32_t*)d_colormap, entries, data_min, r32, normalize,
+               (uint32_t*)d_out);
+    return URH_OK;
 }

@@ -98,10 +98,15 @@ class Filter(object):
 
     @staticmethod
     def fft_convolve_1d(x: np.ndarray, h: np.ndarray):
-        """Filter.py:69-82 — centred crop of the full convolution (the reference computes it with a power-of-two FFT;
-        here it is a direct convolution on the GPU, same values up to rounding)."""
+        """Filter.py:69-82 — centred crop of the full convolution (the reference computes it with a power-of-two FFT in
+        complex128; here it is a direct convolution on the GPU with complex128 taps and double accumulation, returned as
+        complex64 — what every reference caller casts the result to (IQArray) — i.e. the values agree to 1e-5 of the signal
+        scale, DESIGN.md 4.5, not to float64 precision).  len(h) <= 2 gives too_much == 0 and the reference's
+        ``result[0:-0]`` is EMPTY: reproduced."""
         n = len(x) + len(h) - 1
         too_much = (n - len(x)) // 2
+        if too_much == 0:
+            return np.zeros(0, dtype=np.complex64)
         return Filter._convolve_full_slice(x, h, too_much, n - 2 * too_much)
 
     @staticmethod

@@ -60,6 +60,46 @@ class ProtocolAnalyzer(object):
             rssi = np.mean(signal.iq_array.subarray(middle, middle + signal.samples_per_symbol).magnitudes_normalized)
             self.messages.append(LiteMessage(bits, pause, bit_sample_pos[i], rssi))
 
+    # -- per-bit frequency estimation (ProtocolAnalyzer.py:416-447, 570-632) -------------------------------------------
+    def get_samplepos_of_bitseq(self, start_message: int, start_index: int, end_message: int, end_index: int, include_pause: bool):
+        try:
+            if start_message > end_message:
+                start_message, end_message = end_message, start_message
+            if start_index >= len(self.messages[start_message].bit_sample_pos) - 1:
+                start_index = len(self.messages[start_message].bit_sample_pos) - 1
+                if not include_pause:
+                    start_index -= 1
+            if end_index >= len(self.messages[end_message].bit_sample_pos) - 1:
+                end_index = len(self.messages[end_message].bit_sample_pos) - 1
+                if not include_pause:
+                    end_index -= 1
+            start = self.messages[start_message].bit_sample_pos[start_index]
+            num_samples = self.messages[end_message].bit_sample_pos[end_index] - start
+            return start, num_samples
+        except (KeyError, IndexError):
+            return -1, -1
+
+    def estimate_frequency_for_one(self, sample_rate: float, nbits=42) -> float:
+        return self.__estimate_frequency_for_bit(True, sample_rate, nbits)
+
+    def estimate_frequency_for_zero(self, sample_rate: float, nbits=42) -> float:
+        return self.__estimate_frequency_for_bit(False, sample_rate, nbits)
+
+    def __estimate_frequency_for_bit(self, bit: bool, sample_rate: float, nbits: int) -> float:
+        """mean of Signal.estimate_frequency (FFT arg-max on the device, urh_fft_argmax) over at most nbits bits equal to `bit`"""
+        if nbits == 0:
+            return 0
+        assert self.signal is not None
+        frequencies = []
+        for i, message in enumerate(self.messages):
+            for j, msg_bit in enumerate(message.plain_bits):
+                if msg_bit == bit:
+                    start, num_samples = self.get_samplepos_of_bitseq(i, j, i, j + 1, False)
+                    frequencies.append(self.signal.estimate_frequency(start, start + num_samples, sample_rate))
+                    if len(frequencies) == nbits:
+                        return np.mean(frequencies)
+        return np.mean(frequencies) if frequencies else 0
+
     @staticmethod
     def _ppseq_to_bits_device(ppseq, samples_per_symbol, bits_per_symbol, write_bit_sample_pos=True, pause_threshold=8):
         """_ppseq_to_bits with the row loop on the GPU (bits.cu); same return structure as the reference's."""

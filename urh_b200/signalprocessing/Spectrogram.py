@@ -1,5 +1,6 @@
-"""``Spectrogram`` numerics (reference: src/urh/signalprocessing/Spectrogram.py:94-162).  STFT + dB on the GPU
-(spectrogram.cu, cuFFT for the FFT only).  The Qt image / colormap part of the reference class is GUI and out of scope."""
+"""``Spectrogram`` numerics (reference: src/urh/signalprocessing/Spectrogram.py:94-206).  STFT + dB on the GPU
+(spectrogram.cu: one fused kernel for power-of-two windows, cuFFT for the FFT only otherwise) and the BGRA colormap look-up.
+The QImage wrapping of the reference class is GUI and out of scope."""
 import ctypes as C
 import math
 
@@ -74,3 +75,22 @@ class Spectrogram(object):
     def calculate_spectrogram(self, samples: np.ndarray = None) -> np.ndarray:
         """fliplr(arr2decibel(fftshift(stft).astype(complex64))), float32 (Spectrogram.py:156-162)"""
         return self._run(self.samples if samples is None else samples, 1)
+
+    @staticmethod
+    def apply_bgra_lookup(data: np.ndarray, colormap, data_min=None, data_max=None, normalize=True) -> np.ndarray:
+        """Spectrogram.py:192-206 on the GPU: uint8 [cols, rows, 4] image of ``data.T`` through ``colormap`` (entries x 4 bytes BGRA)"""
+        if normalize and (data_min is None or data_max is None):
+            raise ValueError("Can't normalize without data min and data max")
+        ctx = _lib.default_context()
+        on_device = isinstance(data, DeviceArray)
+        d = data if on_device else to_device(np.ascontiguousarray(data, dtype=np.float32), ctx)
+        rows, cols = d.shape
+        cmap = np.ascontiguousarray(colormap, dtype=np.uint8)
+        if cmap.ndim != 2 or cmap.shape[1] != 4:
+            raise ValueError("colormap must be entries x 4 bytes (blue, green, red, alpha)")
+        d_map = to_device(cmap, ctx)
+        out = DeviceArray(ctx, (cols, rows, 4), np.uint8)
+        ctx.check(ctx.lib.urh_bgra_lookup(ctx.handle, C.c_void_p(d.ptr), rows, cols, C.c_void_p(d_map.ptr), len(cmap),
+                                          float(data_min) if normalize else 0.0, float(data_max) if normalize else 1.0, int(bool(normalize)),
+                                          C.c_void_p(out.ptr)))
+        return out if on_device else out.get()
