@@ -498,12 +498,15 @@ def main():
         if world > 1:
             sb2 = udist.ShardBuffer(ctx, n, np.float32)
             halo = sb.halo.get()
+            rows_pinned = PinnedArray((n // 64 + 1024, 2), np.int64, ctx)
 
             def step_e2e():
-                sb2.shard.set_async(host.array)
                 sb2.halo.set(halo)
                 if args.center == "detect":
-                    return udist.demod_center_digitize_distributed(ctx, rank, world, sb2, offset, n_total, NOISE_MAG, "FSK", TOL, SPS, d_qad)[1]
+                    # this rank's shard streamed from pinned host memory (chunked upload overlapped with the demodulation)
+                    return udist.demod_center_digitize_distributed(ctx, rank, world, sb2, offset, n_total, NOISE_MAG, "FSK", TOL, SPS, d_qad,
+                                                                   host_iq=host.array, rows_out=rows_pinned.array)[1]
+                sb2.shard.set_async(host.array)
                 return udist.demod_digitize_distributed(ctx, rank, world, sb2, offset, n_total, NOISE_MAG, "FSK", CENTER, TOL, SPS)
         else:
             d_e2e = DeviceArray(ctx, (n, 2), np.float32)

@@ -202,6 +202,10 @@ int urh_demod_center_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t
 int urh_demod_center_digitize_host(urh_ctx* ctx, const void* h_iq, int dtype, int64_t n, float noise_mag, int mod_type,
                                    uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size, int64_t chunk_samples,
                                    void* d_iq_scratch, float* d_qad_out, double* center, int* center_state, int64_t* k);
+int urh_shard_demod_center_digitize_host(urh_ctx* ctx, const void* h_iq, int dtype, int64_t n, int has_halo, float noise_mag,
+                                         int mod_type, uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size,
+                                         int64_t chunk_samples, void* d_iq_scratch, float* d_qad_out, int64_t global_offset,
+                                         int64_t n_total, double* center, int* center_state, int64_t* k);
 int urh_shard_demod_center_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int has_halo, float noise_mag,
                                     int mod_type, uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size,
                                     float* d_qad_out, int64_t global_offset, int64_t n_total, double* center,

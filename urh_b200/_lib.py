@@ -112,6 +112,8 @@ SIGNATURES = {
     "urh_demod_center_digitize": (i32, [vp, vp, i32, i64, f32, i32, u16, u32, i64, vp, C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(i64)]),
     "urh_demod_center_digitize_host": (i32, [vp, vp, i32, i64, f32, i32, u16, u32, i64, i64, vp, vp, C.POINTER(C.c_double), C.POINTER(i32),
                                              C.POINTER(i64)]),
+    "urh_shard_demod_center_digitize_host": (i32, [vp, vp, i32, i64, i32, f32, i32, u16, u32, i64, i64, vp, vp, i64, i64, C.POINTER(C.c_double),
+                                                   C.POINTER(i32), C.POINTER(i64)]),
     "urh_shard_demod_center_digitize": (i32, [vp, vp, i32, i64, i32, f32, i32, u16, u32, i64, vp, i64, i64, C.POINTER(C.c_double),
                                               C.POINTER(i32), C.POINTER(i64)]),
     "urh_shard_digitize": (i32, [vp, vp, i32, vp, i64, i32, f32, i32, f32, u16, u32, u8, f32, vp, i64, i64, C.POINTER(i64)]),

@@ -639,6 +639,19 @@ extern "C" int urh_demod_center_digitize_host(urh_ctx* ctx, const void* h_iq, in
                                       false, 0, n, center, center_state, k, h_iq, chunk_samples > 0 ? chunk_samples : ((int64_t)1 << 24));
 }
 
+// ... and for one shard of a sharded capture (the halo sample, if any, must already sit at d_iq_scratch[-1])
+extern "C" int urh_shard_demod_center_digitize_host(urh_ctx* ctx, const void* h_iq, int dtype, int64_t n, int has_halo, float noise_mag,
+                                                    int mod_type, uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size,
+                                                    int64_t chunk_samples, void* d_iq_scratch, float* d_qad_out, int64_t global_offset,
+                                                    int64_t n_total, double* center, int* center_state, int64_t* k) {
+    if (!h_iq || !d_iq_scratch) return URH_ERR_INVALID;
+    URH_CUDA(ctx, cudaEventRecord(ctx->ev_comp[0], ctx->stream));
+    URH_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream[0], ctx->ev_comp[0], 0));
+    return demod_center_digitize_impl(ctx, d_iq_scratch, dtype, n, has_halo, noise_mag, mod_type, tolerance, samples_per_symbol, max_size,
+                                      d_qad_out, true, global_offset, n_total, center, center_state, k, h_iq,
+                                      chunk_samples > 0 ? chunk_samples : ((int64_t)1 << 24));
+}
+
 extern "C" int urh_shard_demod_center_digitize(urh_ctx* ctx, const void* d_iq, int dtype, int64_t n, int has_halo, float noise_mag,
                                                int mod_type, uint16_t tolerance, uint32_t samples_per_symbol, int64_t max_size,
                                                float* d_qad_out, int64_t global_offset, int64_t n_total, double* center,

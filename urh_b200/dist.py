@@ -395,25 +395,38 @@ def detect_center_distributed(ctx, rank, world, sb: ShardBuffer, noise_mag, mod_
 
 
 def demod_center_digitize_distributed(ctx, rank, world, sb: ShardBuffer, global_offset, n_total, noise_mag, mod_type, tolerance,
-                                      samples_per_symbol, d_qad, bits_per_symbol=1, center_spacing=0.1, max_size=None, fetch=True):
+                                      samples_per_symbol, d_qad, bits_per_symbol=1, center_spacing=0.1, max_size=None, fetch=True,
+                                      host_iq=None, rows_out=None, chunk_samples=1 << 24):
     """BASELINE configs[1]/[4] on N GPUs: demod + capture-wide detect_center + digitize of ONE sharded capture, one library
     call per rank (urh_shard_demod_center_digitize).  Exchanges, all NCCL on the context stream with device buffers: kept
     counts (8 B), window partials (32 B), the histogram all-reduce, then the digitizer's three 16-byte all-gathers.
-    The digitizer pass reads the shard's qad (4 B/sample) once the center is known.  -> (center, rows or count)."""
+    The digitizer pass reads the shard's qad (4 B/sample) once the center is known.  -> (center, rows or count).
+    ``host_iq``: this rank's shard in (pinned) host memory: it is streamed into ``sb.shard`` in chunks while the chunks that have
+    landed are demodulated (the halo sample must already be in ``sb.halo``); ``rows_out``: pinned int64 buffer for the rows."""
     lib = ctx.lib
     code = _lib.demod_mod_code(mod_type)
     if bits_per_symbol == 1 and not os.environ.get("URH_B200_DIST_STEPWISE"):
         center, state, k = C.c_double(0.0), C.c_int(0), C.c_int64(0)
-        ctx.check(lib.urh_shard_demod_center_digitize(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, int(rank > 0),
-                                                      float(noise_mag), code, int(tolerance), int(samples_per_symbol),
-                                                      -1 if max_size is None else int(max_size), C.c_void_p(d_qad.ptr), int(global_offset),
-                                                      int(n_total), C.byref(center), C.byref(state), C.byref(k)))
+        if host_iq is not None:
+            ctx.check(lib.urh_shard_demod_center_digitize_host(ctx.handle, host_iq.ctypes.data_as(C.c_void_p), _lib.dtype_code(sb.dtype), sb.n,
+                                                               int(rank > 0), float(noise_mag), code, int(tolerance), int(samples_per_symbol),
+                                                               -1 if max_size is None else int(max_size), int(chunk_samples),
+                                                               C.c_void_p(sb.shard.ptr), C.c_void_p(d_qad.ptr), int(global_offset), int(n_total),
+                                                               C.byref(center), C.byref(state), C.byref(k)))
+        else:
+            ctx.check(lib.urh_shard_demod_center_digitize(ctx.handle, C.c_void_p(sb.shard.ptr), _lib.dtype_code(sb.dtype), sb.n, int(rank > 0),
+                                                          float(noise_mag), code, int(tolerance), int(samples_per_symbol),
+                                                          -1 if max_size is None else int(max_size), C.c_void_p(d_qad.ptr), int(global_offset),
+                                                          int(n_total), C.byref(center), C.byref(state), C.byref(k)))
         if state.value == 0:
             return None, (np.zeros((0, 2), dtype=np.int64) if fetch else 0)
         if state.value == 1:
             if not fetch:
                 return float(center.value), int(k.value)
-            rows = np.empty((k.value, 2), dtype=np.int64)
+            if rows_out is not None and rows_out.dtype == np.int64 and rows_out.size >= 2 * k.value:
+                rows = rows_out.reshape(-1)[: 2 * k.value].reshape(k.value, 2)
+            else:
+                rows = np.empty((k.value, 2), dtype=np.int64)
             if k.value:
                 ctx.check(lib.urh_fetch_pulses(ctx.handle, rows.ctypes.data_as(C.c_void_p), k.value))
             return float(center.value), rows
