@@ -180,6 +180,143 @@ __global__ void __launch_bounds__(THREADS) k_stft_fused(const float2* __restrict
     }
 }
 
+// ---- radix-16 variant (W = 256, 1024, 4096): two radix-4 levels per pass held in registers, so a frame crosses shared memory
+// three times (1024 = 16 * 16 * 4) instead of five: the radix-4 kernel above is bound by shared-memory bandwidth.
+// One thread owns 16 points of a pass; W / 16 threads per frame.  Both buffers are padded by one element every 16 (P(i)) so that
+// the stride-16 stores of the first pass do not pile onto the same banks.
+__device__ __forceinline__ int stft_pad(int i) { return i + (i >> 4); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul_mi(double2 a) { return make_double2(a.y, -a.x); }   // a * (-i)
+// forward DFT of length 4, in place
+__device__ __forceinline__ void dft4(double2& x0, double2& x1, double2& x2, double2& x3) {
+    const double2 s02 = cadd(x0, x2), d02 = csub(x0, x2), s13 = cadd(x1, x3), d13 = cmul_mi(csub(x1, x3));
+    x0 = cadd(s02, s13); x1 = cadd(d02, d13); x2 = csub(s02, s13); x3 = csub(d02, d13);
+}
+// forward DFT of length 16, in place: v[c + 4 r'] -> columns, twiddle w16^(c r), rows; output y[r + 4 s] (natural order)
+__device__ __forceinline__ void dft16(double2 (&v)[16]) {
+    const double C1 = 0.92387953251128675613, S1 = 0.38268343236508977173, H = 0.70710678118654752440;
+#pragma unroll
+    for (int c = 0; c < 4; c++) dft4(v[c], v[c + 4], v[c + 8], v[c + 12]);   // now v[c + 4 r] = u_c[r]
+    // u_c[r] *= w16^(c r)
+    v[1 + 4] = cmul(v[1 + 4], make_double2(C1, -S1));    // c=1, r=1: w^1
+    v[1 + 8] = cmul(v[1 + 8], make_double2(H, -H));      // w^2
+    v[1 + 12] = cmul(v[1 + 12], make_double2(S1, -C1));  // w^3
+    v[2 + 4] = cmul(v[2 + 4], make_double2(H, -H));      // c=2, r=1: w^2
+    v[2 + 8] = cmul_mi(v[2 + 8]);                        // w^4 = -i
+    v[2 + 12] = cmul(v[2 + 12], make_double2(-H, -H));   // w^6
+    v[3 + 4] = cmul(v[3 + 4], make_double2(S1, -C1));    // c=3, r=1: w^3
+    v[3 + 8] = cmul(v[3 + 8], make_double2(-H, -H));     // w^6
+    v[3 + 12] = cmul(v[3 + 12], make_double2(-C1, S1));  // w^9
+    // rows: y[r + 4 s] = sum_c u_c[r] w4^(c s): DFT4 over c for each r; u_c[r] sits at v[c + 4 r]
+#pragma unroll
+    for (int r = 0; r < 4; r++) dft4(v[4 * r], v[4 * r + 1], v[4 * r + 2], v[4 * r + 3]);   // v[4 r + s] = y[r + 4 s]
+}
+
+template <int LOG2W, int MODE>
+__global__ void __launch_bounds__((1 << LOG2W) / 16) k_stft_r16(const float2* __restrict__ x, int64_t n, int hop,
+                                                               const double* __restrict__ window, const double2* __restrict__ tw,
+                                                               int64_t nframes, void* __restrict__ out_) {
+    constexpr int W = 1 << LOG2W;
+    constexpr int T = W / 16;                 // threads per frame
+    constexpr int PADW = W + W / 16;
+    extern __shared__ double2 s_buf[];        // two padded buffers
+    double2* a = s_buf;
+    double2* b = s_buf + PADW;
+    const int tid = threadIdx.x;
+    const int64_t f = blockIdx.x;
+    const int64_t base = f * hop;
+    {
+        float2 sm[16];
+        double g[16];
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const int w = tid + T * m;
+            const int64_t i = base + w;
+            sm[m] = (i < n) ? x[i] : make_float2(0.0f, 0.0f);
+            g[m] = window[w];
+        }
+#pragma unroll
+        for (int m = 0; m < 16; m++) a[stft_pad(tid + T * m)] = make_double2((double)sm[m].x * g[m], (double)sm[m].y * g[m]);
+    }
+    __syncthreads();
+    constexpr int NPASS16 = LOG2W / 4;
+#pragma unroll
+    for (int st = 0; st < NPASS16; st++) {
+        const int ns = 1 << (4 * st);
+        const int k = tid & (ns - 1);
+        const int tstep = W / (16 * ns);
+        double2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; m++) v[m] = a[stft_pad(tid + T * m)];
+        if (ns > 1) {
+#pragma unroll
+            for (int m = 1; m < 16; m++) v[m] = cmul(v[m], tw[m * k * tstep]);
+        }
+        dft16(v);   // v[4 r + s] = y[r + 4 s]
+        const int o = ((tid - k) << 4) + k;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) b[stft_pad(o + ns * (r + 4 * q))] = v[4 * r + q];
+        __syncthreads();
+        double2* t = a; a = b; b = t;
+    }
+    if ((LOG2W & 3) == 2) {   // one radix-4 pass left (sub-transforms of length W / 4)
+        constexpr int ns = W / 4;
+        double2 y[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int j = tid + T * r;   // butterfly index < W / 4; k = j (ns = W / 4 > j)
+            double2 v0 = a[stft_pad(j)], v1 = a[stft_pad(j + ns)], v2 = a[stft_pad(j + 2 * ns)], v3 = a[stft_pad(j + 3 * ns)];
+            v1 = cmul(v1, tw[j]);
+            v2 = cmul(v2, tw[2 * j]);
+            v3 = cmul(v3, tw[3 * j]);
+            dft4(v0, v1, v2, v3);
+            y[r][0] = v0; y[r][1] = v1; y[r][2] = v2; y[r][3] = v3;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) b[stft_pad(tid + T * r + ns * q)] = y[r][q];
+        __syncthreads();
+        double2* t = a; a = b; b = t;
+    }
+    const double inv = 1.0 / (double)W;
+    if (MODE == 0) {
+        double2* out = (double2*)out_ + f * W;
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const int w = tid + T * m;
+            const double2 v = a[stft_pad(w)];
+            out[w] = make_double2(v.x * inv, v.y * inv);
+        }
+    } else {
+        float* out = (float*)out_ + f * W;
+        constexpr int shift = (W + 1) / 2;
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const int j = tid + T * m;
+            const int src = ((W - 1 - j) + shift) & (W - 1);   // fliplr, then fftshift
+            const double2 v = a[stft_pad(src)];
+            const float re = (float)(v.x * inv), im = (float)(v.y * inv);
+            out[j] = __fmul_rn(10.0f, log10f(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im))));
+        }
+    }
+}
+
+template <int LOG2W, int MODE>
+static int stft_r16_launch(urh_ctx* ctx, const float* d_x, int64_t n, int hop, const double* d_window, const double2* tw,
+                           int64_t num_frames, void* d_out) {
+    constexpr int W = 1 << LOG2W;
+    const size_t smem = (size_t)2 * (W + W / 16) * sizeof(double2);
+    if (smem > 48 * 1024)
+        URH_CUDA(ctx, cudaFuncSetAttribute(k_stft_r16<LOG2W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    URH_LAUNCH(ctx, (k_stft_r16<LOG2W, MODE>), (unsigned)num_frames, W / 16, smem, (const float2*)d_x, n, hop, d_window, tw, num_frames,
+               d_out);
+    return URH_OK;
+}
+
 template <int LOG2W, int MODE>
 static int stft_fused_launch(urh_ctx* ctx, const float* d_x, int64_t n, int hop, const double* d_window, const double2* tw,
                              int64_t num_frames, void* d_out) {
@@ -206,6 +343,14 @@ static int stft_fused(urh_ctx* ctx, const float* d_x, int64_t n, int W, int hop,
     case L:                                                                                                                   \
         return mode == 0 ? stft_fused_launch<L, 0>(ctx, d_x, n, hop, d_window, (const double2*)tw, num_frames, d_out)         \
                          : stft_fused_launch<L, 1>(ctx, d_x, n, hop, d_window, (const double2*)tw, num_frames, d_out);
+    if (!getenv("URH_B200_STFT_RADIX4")) {   // 16 | W: three passes through shared memory instead of five
+        if (log2w == 10) return mode == 0 ? stft_r16_launch<10, 0>(ctx, d_x, n, hop, d_window, (const double2*)tw, num_frames, d_out)
+                                          : stft_r16_launch<10, 1>(ctx, d_x, n, hop, d_window, (const double2*)tw, num_frames, d_out);
+        if (log2w == 12) return mode == 0 ? stft_r16_launch<12, 0>(ctx, d_x, n, hop, d_window, (const double2*)tw, num_frames, d_out)
+                                          : stft_r16_launch<12, 1>(ctx, d_x, n, hop, d_window, (const double2*)tw, num_frames, d_out);
+        if (log2w == 8) return mode == 0 ? stft_r16_launch<8, 0>(ctx, d_x, n, hop, d_window, (const double2*)tw, num_frames, d_out)
+                                         : stft_r16_launch<8, 1>(ctx, d_x, n, hop, d_window, (const double2*)tw, num_frames, d_out);
+    }
     switch (log2w) {
         STFT_CASE(7) STFT_CASE(8) STFT_CASE(9) STFT_CASE(10) STFT_CASE(11) STFT_CASE(12)
         default: break;
