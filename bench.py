@@ -285,7 +285,7 @@ def main():
     world = env_int("WORLD_SIZE", 1)
     n = 1 << args.log2n
     layout = ("2^%d samples on one GPU" % args.log2n if world == 1 else
-              "ONE capture of %d x 2^%d samples sharded by contiguous range (1-sample halo, NCCL run stitching)" % (world, args.log2n))
+              "ONE capture of %d x 2^%d samples sharded by contiguous range (1-sample halo, run stitching across shards)" % (world, args.log2n))
     workload = ("2-FSK complex64, %s @2MS/s sps=100 +-100kHz AWGN sigma=0.01 bursts+gaps; %s (tol=5, noise=0.05)"
                 % (layout, "demod + detect_center (capture-wide) + digitize" if args.center == "detect"
                    else "fused demod+digitize, center=0 given"))
@@ -342,6 +342,8 @@ def main():
     if world > 1:
         hx = udist.HostExchange()
         udist.init_nccl(ctx, hx)
+        base["config"]["exchange"] = ("NVLink peer mailboxes (device-resident, stream-ordered)" if getattr(ctx, "p2p", False)
+                                      else "NCCL (stream-ordered)")
         udist.exchange_halo(ctx, hx, sb)
 
     from urh_b200.ainterpretation import AutoInterpretation as AI

@@ -267,6 +267,14 @@ int urh_p2p_create(urh_ctx* ctx, char* out_handle64);
 int urh_p2p_open(urh_ctx* ctx, const char* handles, int rank, int world);
 int urh_p2p_close(urh_ctx* ctx);
 int urh_p2p_allgather_host(urh_ctx* ctx, const void* h_send, void* h_recv, size_t bytes_per_rank);
+/* The same exchange between DEVICE buffers, enqueued on the context stream with no host synchronisation (what the sharded chains
+ * urh_shard_* use between their kernels when the mailboxes are open; NCCL otherwise): all-gather of 8..240 bytes per rank (a multiple
+ * of 8); sum over ranks of min(*d_count, max_words) uint64 words (max_words <= 6000, d_out must not alias d_in, d_count a device
+ * pointer or NULL).  A peer that does not show up within ~5 s raises a flag instead of hanging the GPU: urh_p2p_check, called after
+ * the next synchronisation, returns URH_ERR_CUDA and closes the mailboxes. */
+int urh_p2p_allgather_dev(urh_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
+int urh_p2p_allreduce_u64_dev(urh_ctx* ctx, const void* d_in, void* d_out, const int64_t* d_count, int max_words);
+int urh_p2p_check(urh_ctx* ctx);
 
 /* ---- measurement utilities (not part of the reference's API surface) -------------------------------- */
 /* CUDA-event timing of the dominant (dense, sample-rate) kernel of the last demod/digitize call */

@@ -28,7 +28,35 @@ def main():
     # NVLink peer mailboxes == NCCL for the few-bytes all-gathers (and they were actually opened)
     import ctypes as C
     rng_x = np.random.default_rng(1000 + rank)
-    if getattr(ctx, "p2p", False):   # opt-in (URH_B200_P2P=1)
+    if rank == 0:
+        print("DIST_GPU p2p mailboxes:", "open" if getattr(ctx, "p2p", False) else "not open (NCCL only)", flush=True)
+    if getattr(ctx, "p2p", False):
+        # device-resident exchanges (what the sharded chains use between their kernels) against NCCL
+        for it in range(200):
+            words = 1 + it % 30
+            send = rng_x.integers(-2**62, 2**62, words).astype(np.int64)
+            d_send = to_device(send, ctx)
+            d_a = DeviceArray(ctx, (world, words), np.int64)
+            d_b = DeviceArray(ctx, (world, words), np.int64)
+            ctx.check(ctx.lib.urh_p2p_allgather_dev(ctx.handle, C.c_void_p(d_send.ptr), C.c_void_p(d_a.ptr), send.nbytes))
+            ctx.check(ctx.lib.urh_nccl_allgather(ctx.handle, C.c_void_p(d_send.ptr), C.c_void_p(d_b.ptr), send.nbytes))
+            a, b = d_a.get(), d_b.get()
+            ctx.check(ctx.lib.urh_p2p_check(ctx.handle))
+            if not np.array_equal(a, b) or not np.array_equal(a[rank], send):
+                failures.append(("p2p device allgather", it))
+        for it, cnt in enumerate([1, 7, 256, 1000, 6000, 6000, 33]):
+            vals = rng_x.integers(0, 2**40, 6000).astype(np.int64)
+            d_in = to_device(vals, ctx)
+            d_out = DeviceArray(ctx, (6000,), np.int64)
+            d_out.zero()
+            d_cnt = to_device(np.array([cnt], np.int64), ctx)
+            ctx.check(ctx.lib.urh_p2p_allreduce_u64_dev(ctx.handle, C.c_void_p(d_in.ptr), C.c_void_p(d_out.ptr), C.c_void_p(d_cnt.ptr), 6000))
+            d_ref = to_device(vals, ctx)
+            ctx.check(ctx.lib.urh_nccl_allreduce_i64(ctx.handle, C.c_void_p(d_ref.ptr), 6000, 0))
+            got, ref = d_out.get(), d_ref.get()
+            ctx.check(ctx.lib.urh_p2p_check(ctx.handle))
+            if not np.array_equal(got[:cnt], ref[:cnt]) or np.any(got[cnt:] != 0):
+                failures.append(("p2p device allreduce", it, cnt))
         for it in range(300):
             k = 1 + it % 6
             send = rng_x.integers(-2**62, 2**62, k).astype(np.int64)

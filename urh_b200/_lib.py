@@ -109,6 +109,9 @@ SIGNATURES = {
     "urh_p2p_open": (i32, [vp, vp, i32, i32]),
     "urh_p2p_close": (i32, [vp]),
     "urh_p2p_allgather_host": (i32, [vp, vp, vp, szt]),
+    "urh_p2p_allgather_dev": (i32, [vp, vp, vp, szt]),
+    "urh_p2p_allreduce_u64_dev": (i32, [vp, vp, vp, vp, i32]),
+    "urh_p2p_check": (i32, [vp]),
     "urh_demod_center_digitize": (i32, [vp, vp, i32, i64, f32, i32, u16, u32, i64, vp, C.POINTER(C.c_double), C.POINTER(i32), C.POINTER(i64)]),
     "urh_demod_center_digitize_host": (i32, [vp, vp, i32, i64, f32, i32, u16, u32, i64, i64, vp, vp, C.POINTER(C.c_double), C.POINTER(i32),
                                              C.POINTER(i64)]),

@@ -378,22 +378,25 @@ __device__ __forceinline__ void hist_miss(HistCache& hc, const HistBins& hb, uns
 }
 
 template <bool SMEM, bool FAST>
-__device__ __forceinline__ void hist_put(HistCache& hc, const HistBins& hb, unsigned int* s_hist, unsigned long long* hist, float f) {
-    // per entry: two compares chained into one predicate and a predicated increment (spelled out in PTX: the compiler
-    // otherwise turns each increment into select + add + move); miss = inside the histogram's range but in no cached bin
+__device__ __forceinline__ void hist_put(HistCache& hc, const HistBins& hb, unsigned int* s_hist, unsigned long long* hist, float f,
+                                         unsigned one) {
+    // per entry: two compares chained into one predicate and a predicated increment, spelled out in PTX.  The kernel is bound by
+    // the ALU pipe (FSETP, predicate logic: ncu r02), so the increments are multiply-adds by a run-time 1 - IMAD runs on the
+    // FMA pipe - and the hit path tests the lower validity bound only (noise samples sit below it; a sample above the last edge
+    // falls through to the miss path, which tests both bounds).  miss = not below the range and in no cached bin.
     unsigned miss;
     asm("{\n\t.reg .pred p0, p1, p2, p3, pv;\n\t"
-        "setp.ge.f32 p0, %5, %6;\n\tsetp.lt.and.f32 p0, %5, %7, p0;\n\t@p0 add.u32 %0, %0, 1;\n\t"
-        "setp.ge.f32 p1, %5, %8;\n\tsetp.lt.and.f32 p1, %5, %9, p1;\n\t@p1 add.u32 %1, %1, 1;\n\t"
-        "setp.ge.f32 p2, %5, %10;\n\tsetp.lt.and.f32 p2, %5, %11, p2;\n\t@p2 add.u32 %2, %2, 1;\n\t"
-        "setp.ge.f32 p3, %5, %12;\n\tsetp.lt.and.f32 p3, %5, %13, p3;\n\t@p3 add.u32 %3, %3, 1;\n\t"
+        "setp.ge.f32 p0, %5, %6;\n\tsetp.lt.and.f32 p0, %5, %7, p0;\n\t@p0 mad.lo.u32 %0, %0, %15, %15;\n\t"
+        "setp.ge.f32 p1, %5, %8;\n\tsetp.lt.and.f32 p1, %5, %9, p1;\n\t@p1 mad.lo.u32 %1, %1, %15, %15;\n\t"
+        "setp.ge.f32 p2, %5, %10;\n\tsetp.lt.and.f32 p2, %5, %11, p2;\n\t@p2 mad.lo.u32 %2, %2, %15, %15;\n\t"
+        "setp.ge.f32 p3, %5, %12;\n\tsetp.lt.and.f32 p3, %5, %13, p3;\n\t@p3 mad.lo.u32 %3, %3, %15, %15;\n\t"
         "or.pred p0, p0, p1;\n\tor.pred p2, p2, p3;\n\tor.pred p0, p0, p2;\n\t"
-        "setp.ge.f32 pv, %5, %14;\n\tsetp.le.and.f32 pv, %5, %15, pv;\n\t"
+        "setp.ge.f32 pv, %5, %14;\n\t"
         "and.pred pv, pv, !p0;\n\t"
         "selp.u32 %4, 1, 0, pv;\n\t}"
         : "+r"(hc.c0), "+r"(hc.c1), "+r"(hc.c2), "+r"(hc.c3), "=r"(miss)
         : "f"(f), "f"(hc.lo0), "f"(hc.hi0), "f"(hc.lo1), "f"(hc.hi1), "f"(hc.lo2), "f"(hc.hi2), "f"(hc.lo3), "f"(hc.hi3),
-          "f"(hb.f_min), "f"(hb.f_hi));
+          "f"(hb.f_min), "r"(one));
     if (miss) hist_miss<SMEM, FAST>(hc, hb, s_hist, hist, f);
 }
 
@@ -429,34 +432,32 @@ __device__ __forceinline__ void hist_interior_body(const float* __restrict__ x, 
     const int64_t t_first = win[0] + 1, t_end = win[1];
     const int64_t gw = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * 8;
     const bool vec = (((uintptr_t)x) & 15) == 0;
+    const unsigned one = blockDim.x >> 8;   // 1 (256 threads), but not a compile-time constant: see hist_put
     if (win[0] >= 0) {   // < 0: empty window
         for (int64_t t = t_first + gw; t < t_end; t += nw) {
             if (prefix[t + 1] == prefix[t]) continue;   // no kept sample in this tile (silence): nothing to count, nothing to read
             const int64_t base = t * URH_TILE;   // interior tiles are full tiles (t < last tile)
             if (vec) {
                 const float4* p = (const float4*)(x + base) + lane;
-                constexpr int ITERS = URH_TILE / 128, RB = 2;   // RB rows being binned + RB rows in flight
-                float4 cur[RB], nxt[RB];
+                constexpr int ITERS = URH_TILE / 128, DEPTH = 4;   // a ring of four 512-byte rows in flight per warp
+                float4 buf[DEPTH];
 #pragma unroll
-                for (int j = 0; j < RB; j++) cur[j] = __ldg(p + j * 32);
+                for (int j = 0; j < DEPTH; j++) buf[j] = __ldg(p + j * 32);
 #pragma unroll 1
-                for (int it = 0; it < ITERS; it += RB) {
-                    if (it + RB < ITERS) {
+                for (int it = 0; it < ITERS; it += DEPTH) {
+                    const bool more = it + DEPTH < ITERS;
 #pragma unroll
-                        for (int j = 0; j < RB; j++) nxt[j] = __ldg(p + (it + RB + j) * 32);
+                    for (int j = 0; j < DEPTH; j++) {
+                        const float4 v = buf[j];
+                        if (more) buf[j] = __ldg(p + (it + DEPTH + j) * 32);
+                        hist_put<SMEM, FAST>(hc, hb, s_hist, hist, v.x, one);
+                        hist_put<SMEM, FAST>(hc, hb, s_hist, hist, v.y, one);
+                        hist_put<SMEM, FAST>(hc, hb, s_hist, hist, v.z, one);
+                        hist_put<SMEM, FAST>(hc, hb, s_hist, hist, v.w, one);
                     }
-#pragma unroll
-                    for (int j = 0; j < RB; j++) {
-                        hist_put<SMEM, FAST>(hc, hb, s_hist, hist, cur[j].x);
-                        hist_put<SMEM, FAST>(hc, hb, s_hist, hist, cur[j].y);
-                        hist_put<SMEM, FAST>(hc, hb, s_hist, hist, cur[j].z);
-                        hist_put<SMEM, FAST>(hc, hb, s_hist, hist, cur[j].w);
-                    }
-#pragma unroll
-                    for (int j = 0; j < RB; j++) cur[j] = nxt[j];
                 }
             } else {
-                for (int j = lane; j < URH_TILE; j += 32) hist_put<SMEM, FAST>(hc, hb, s_hist, hist, x[base + j]);
+                for (int j = lane; j < URH_TILE; j += 32) hist_put<SMEM, FAST>(hc, hb, s_hist, hist, x[base + j], one);
             }
         }
     }
@@ -774,7 +775,7 @@ __global__ void __launch_bounds__(256) k_center_plan(const CenStats* __restrict_
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(256, 4) k_hist_interior_dev(const float* __restrict__ x, int64_t n, const CenterPlan* __restrict__ plan,
+__global__ void __launch_bounds__(256, 3) k_hist_interior_dev(const float* __restrict__ x, int64_t n, const CenterPlan* __restrict__ plan,
                                                           const float* __restrict__ g_fe, unsigned long long* __restrict__ hist,
                                                           const int64_t* __restrict__ prefix) {
     if (plan->state != 1 || (plan->fast != 0) != FAST) return;
@@ -881,7 +882,9 @@ __global__ void __launch_bounds__(256) k_center_pick(const unsigned long long* _
     (void)top_val;
 }
 
-extern "C" int urh_nccl_allgather(urh_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
+int urh_coll_allgather(urh_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);   // nccl.cu: mailboxes or NCCL
+bool urh_p2p_usable(urh_ctx* ctx, size_t bytes_per_rank);
+extern "C" int urh_p2p_allreduce_u64_dev(urh_ctx* ctx, const void* d_in, void* d_out, const int64_t* d_count, int max_words);
 extern "C" int urh_nccl_allreduce_i64(urh_ctx* ctx, int64_t* d_buf, int64_t count, int op);
 
 // The chain.  ts = the demodulator's tile table of d_qad (arena); *d_plan_out stays valid until the next arena reset.
@@ -909,14 +912,14 @@ int urh_center_chain(urh_ctx* ctx, const float* d_qad, int64_t n, const UrhTileS
     URH_CHECK((urhts::scan<int64_t, CenAddI64, ScanKept>(ctx, ntiles, (int64_t)0, CenAddI64(), fk, prefix + ntiles)));
     const int64_t* counts = prefix + ntiles;
     if (world > 1) {
-        URH_CHECK(urh_nccl_allgather(ctx, prefix + ntiles, d_counts, sizeof(int64_t)));
+        URH_CHECK(urh_coll_allgather(ctx, prefix + ntiles, d_counts, sizeof(int64_t)));
         counts = d_counts;
     }
     URH_LAUNCH(ctx, k_center_ranks, 1, 1, 0, counts, rank, world, max_size, plan);
     URH_LAUNCH(ctx, k_center_window, nb, 256, 0, d_qad, n, ts, (const int64_t*)prefix, ntiles, plan, partial);
     const CenStats* parts = &plan->local;
     if (world > 1) {
-        URH_CHECK(urh_nccl_allgather(ctx, &plan->local, d_parts, sizeof(CenStats)));
+        URH_CHECK(urh_coll_allgather(ctx, &plan->local, d_parts, sizeof(CenStats)));
         parts = d_parts;
     }
     URH_LAUNCH(ctx, k_center_plan, 1, 256, 0, parts, world, plan, fe, hist);
@@ -925,8 +928,18 @@ int urh_center_chain(urh_ctx* ctx, const float* d_qad, int64_t n, const UrhTileS
     URH_LAUNCH(ctx, (k_hist_interior_dev<true>), gs, 256, dyn, d_qad, n, (const CenterPlan*)plan, (const float*)fe, hist, (const int64_t*)prefix);
     URH_LAUNCH(ctx, (k_hist_interior_dev<false>), gs, 256, dyn, d_qad, n, (const CenterPlan*)plan, (const float*)fe, hist, (const int64_t*)prefix);
     URH_LAUNCH(ctx, k_hist_window_ends_dev, 2, 256, 0, d_qad, n, (const int64_t*)prefix, (const CenterPlan*)plan, (const float*)fe, hist);
-    if (world > 1) URH_CHECK(urh_nccl_allreduce_i64(ctx, (int64_t*)hist, CEN_MAX_BINS, 0));
-    URH_LAUNCH(ctx, k_center_pick, 1, 256, 0, (const unsigned long long*)hist, plan);
+    const unsigned long long* hist_all = hist;
+    if (world > 1) {
+        if (urh_p2p_usable(ctx, 8)) {   // NVLink mailboxes: only the plan's nbins words travel
+            unsigned long long* hist_sum;
+            URH_CHECK(urh_arena(ctx, (size_t)CEN_MAX_BINS, &hist_sum));
+            URH_CHECK(urh_p2p_allreduce_u64_dev(ctx, hist, hist_sum, (const int64_t*)&plan->nbins, CEN_MAX_BINS));
+            hist_all = hist_sum;
+        } else {
+            URH_CHECK(urh_nccl_allreduce_i64(ctx, (int64_t*)hist, CEN_MAX_BINS, 0));
+        }
+    }
+    URH_LAUNCH(ctx, k_center_pick, 1, 256, 0, hist_all, plan);
     ctx->center_prefix = prefix;
     ctx->center_ts = ts;
     ctx->center_n = n;

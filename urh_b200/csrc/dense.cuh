@@ -206,11 +206,13 @@ struct UrhRunTracker {
     int tol;
     int run_start, run_cls, first_cls, head_len, ncand, carry_cls;
     bool is_head;
+    uint32_t cm_n, cm_a;   // feed_masks: the open run's class bits as full words
     uint32_t* stage;   // this tile's staging slots
 
     __device__ __forceinline__ void init(int tol_, uint32_t* stage_) {
         tol = tol_; stage = stage_;
         run_start = 0; run_cls = -2; first_cls = -2; head_len = 0; ncand = 0; carry_cls = -2; is_head = true;
+        cm_n = 0xffffffffu; cm_a = 0xffffffffu;
     }
     __device__ __forceinline__ void emit(int pos, int cls, int lane) {
         if (lane == 0) stage[ncand] = ((uint32_t)pos << 16) | (uint32_t)(cls + 1);
@@ -227,6 +229,63 @@ struct UrhRunTracker {
         const uint32_t m1 = __ballot_sync(URH_FULL_MASK, b1);
         if ((m0 | m1) == 0u) return;
         walk(it, m0, m1, c0, c1, lane);
+    }
+    // Binary classifiers (one threshold): the classes of a 64-group as four WARP MASKS - n0/n1: sample 2l / 2l+1 is noise (class -1),
+    // a0/a1: it is above the threshold (never set together with the noise bit).  The boundary masks are bit arithmetic on the masks:
+    // warp-uniform work (no shuffles, no per-lane class integers), the per-lane classes are only formed when a boundary exists.
+    // Full 64-groups only; do not mix with feed() inside one tile (feed() carries the previous class in carry_cls, this one in run_cls).
+    __device__ __forceinline__ void feed_masks(int it, uint32_t n0, uint32_t a0, uint32_t n1, uint32_t a1, int lane) {
+        // no boundary <=> all 64 samples repeat the open run's class: cm_n / cm_a are that class's bits spread over a word (the
+        // impossible pair ~0 / ~0 before the tile's first sample, so the first group always takes the long way)
+        if ((((n0 ^ cm_n) | (n1 ^ cm_n)) | ((a0 ^ cm_a) | (a1 ^ cm_a))) == 0u) return;
+        // class bits of the sample before sample 2l: sample 2(l-1)+1, for lane 0 the previous group's last sample
+        uint32_t m0 = (((n1 << 1) | (cm_n & 1u)) ^ n0) | (((a1 << 1) | (cm_a & 1u)) ^ a0);
+        if (run_cls == -2) m0 |= 1u;                    // the tile's first sample opens the head run
+        uint32_t m1 = (n0 ^ n1) | (a0 ^ a1);
+        feed_masks_slow(it, n0, a0, n1, a1, m0, m1, lane);
+        cm_n = (run_cls < 0) ? 0xffffffffu : 0u;
+        cm_a = (run_cls == 1) ? 0xffffffffu : 0u;
+    }
+    __device__ __forceinline__ void feed_masks_slow(int it, uint32_t n0, uint32_t a0, uint32_t n1, uint32_t a1, uint32_t m0, uint32_t m1,
+                                                    int lane) {
+        const int nb = __popc(m0) + __popc(m1);
+        if (nb == 1 && run_cls != -2 && !is_head) {
+            // the common case of a demodulated signal (one symbol edge in 64 samples, inside the tile): no loop
+            const bool take0 = m0 != 0u;
+            const int l = __ffs(m0 | m1) - 1;
+            const int p = it * 64 + 2 * l + (take0 ? 0 : 1);
+            const uint32_t nbit = ((take0 ? n0 : n1) >> l) & 1u, abit = ((take0 ? a0 : a1) >> l) & 1u;
+            if (p - run_start > tol) emit(run_start + tol, run_cls, lane);
+            run_start = p;
+            run_cls = nbit ? -1 : (int)abit;
+            return;
+        }
+        if (nb > 4) {
+            const int c0 = ((n0 >> lane) & 1u) ? -1 : (int)((a0 >> lane) & 1u);
+            const int c1 = ((n1 >> lane) & 1u) ? -1 : (int)((a1 >> lane) & 1u);
+            walk_parallel(it, m0, m1, c0, c1, lane);
+            return;
+        }
+        while (m0 | m1) {
+            const int l0 = m0 ? (__ffs(m0) - 1) : 64;
+            const int l1 = m1 ? (__ffs(m1) - 1) : 64;
+            const bool take0 = l0 <= l1;
+            const int l = take0 ? l0 : l1;
+            if (take0) m0 &= m0 - 1; else m1 &= m1 - 1;
+            const int p = it * 64 + 2 * l + (take0 ? 0 : 1);
+            const uint32_t nbit = ((take0 ? n0 : n1) >> l) & 1u, abit = ((take0 ? a0 : a1) >> l) & 1u;
+            const int cls_p = nbit ? -1 : (int)abit;
+            if (run_cls == -2) {
+                first_cls = cls_p;
+            } else if (is_head) {
+                head_len = p;
+                is_head = false;
+            } else if (p - run_start > tol) {
+                emit(run_start + tol, run_cls, lane);
+            }
+            run_start = p;
+            run_cls = cls_p;
+        }
     }
     // Same as feed() but with the boundary predicates supplied by the caller (fsk_fast.cuh derives them
     // without materialising class integers for the compare).

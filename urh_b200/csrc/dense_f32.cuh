@@ -5,20 +5,36 @@
 #include "dense.cuh"
 
 // Classifier sources for the stand-alone digitizer / segmenter: float32 samples already in memory.
+// BINARY sources also give the class as two predicates (noise, above) for UrhRunTracker::feed_masks.
 struct SrcQad {  // grab_pulse_lens on a demodulated array
+    static constexpr bool BINARY = false;
     template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C, float) { return urh_classify((float)s, C); }
+    template <typename T> __device__ __forceinline__ static void bits(T, const UrhClassify&, float, bool& nz, bool& ab) { nz = false; ab = false; }
+    template <typename T> __device__ __forceinline__ static bool above(T, float) { return false; }
 };
 struct SrcQad2 {  // the same for a binary digitizer (order 2): no threshold loop, no branches
+    static constexpr bool BINARY = true;
     template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify& C, float thr0) {
         const int c = ((float)s <= thr0) ? 0 : 1;
         return ((float)s == C.noise_value) ? -1 : c;
     }
+    template <typename T> __device__ __forceinline__ static void bits(T s, const UrhClassify& C, float thr0, bool& nz, bool& ab) {
+        nz = (float)s == C.noise_value;
+        ab = !((float)s <= thr0) && !nz;
+    }
+    template <typename T> __device__ __forceinline__ static bool above(T s, float thr0) { return !((float)s <= thr0); }   // tile without noise
 };
 struct SrcAbove {  // segment_messages_from_magnitudes: class 1 = above noise (auto_interpretation.pyx:79)
+    static constexpr bool BINARY = true;
     template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify&, float thr0) { return (s > (T)thr0) ? 1 : 0; }
+    template <typename T> __device__ __forceinline__ static void bits(T s, const UrhClassify&, float thr0, bool& nz, bool& ab) { nz = false; ab = s > (T)thr0; }
+    template <typename T> __device__ __forceinline__ static bool above(T s, float thr0) { return s > (T)thr0; }
 };
 struct SrcCenter {  // get_plateau_lengths: -1/1 around center (auto_interpretation.pyx:183,197) as 0/1
+    static constexpr bool BINARY = true;
     template <typename T> __device__ __forceinline__ static int cls(T s, const UrhClassify&, float thr0) { return (s <= (T)thr0) ? 0 : 1; }
+    template <typename T> __device__ __forceinline__ static void bits(T s, const UrhClassify&, float thr0, bool& nz, bool& ab) { nz = false; ab = !(s <= (T)thr0); }
+    template <typename T> __device__ __forceinline__ static bool above(T s, float thr0) { return !(s <= (T)thr0); }
 };
 
 template <typename T> struct UrhVec2;
@@ -57,18 +73,37 @@ k_dense_f32(const T* __restrict__ x, int64_t n, int vec_in, const __grid_constan
         typedef typename UrhVec2<T>::type V;
         const V* p = (const V*)(x + tile_start) + lane;  // 64-group `it` -> p[it * 32]
         constexpr int ITERS = URH_TILE / 64;
+        // the demodulator counted the tile's kept samples (> -4): all kept <=> no sample carries the noise sentinel (<= -4), and
+        // the noise masks (half of the compares, votes and mask arithmetic) are known to be zero
+        const bool no_noise = SRC::BINARY && tile_stats && cls.noise_value <= -4.0f && tile_stats[tile].cnt == URH_TILE;
+        // eight 64-groups in flight per warp (four being classified, four being loaded).  (A ring of eight, each register refilled
+        // as soon as it is consumed, was slower: eight inlined copies of the boundary path no longer fit the instruction cache.)
         V cur[4], nxt[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) cur[j] = __ldg(p + j * 32);
         if (tile_start == 0 && lane == 0 && init_cls) *init_cls = (int16_t)(((float)cur[0].x == cls.noise_value) ? -1 : cls_of_zero);
+#pragma unroll 1
         for (int it = 0; it < ITERS; it += 4) {
             if (it + 4 < ITERS) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) nxt[j] = __ldg(p + (it + 4 + j) * 32);
             }
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                rt.feed(it + j, SRC::template cls<T>(cur[j].x, cls, thr0), SRC::template cls<T>(cur[j].y, cls, thr0), true, true, lane);
+            for (int j = 0; j < 4; j++) {
+                const V v = cur[j];
+                if (SRC::BINARY && no_noise) {
+                    rt.feed_masks(it + j, 0u, __ballot_sync(URH_FULL_MASK, SRC::template above<T>(v.x, thr0)), 0u,
+                                  __ballot_sync(URH_FULL_MASK, SRC::template above<T>(v.y, thr0)), lane);
+                } else if (SRC::BINARY) {
+                    bool nx, ax, ny, ay;
+                    SRC::template bits<T>(v.x, cls, thr0, nx, ax);
+                    SRC::template bits<T>(v.y, cls, thr0, ny, ay);
+                    rt.feed_masks(it + j, __ballot_sync(URH_FULL_MASK, nx), __ballot_sync(URH_FULL_MASK, ax),
+                                  __ballot_sync(URH_FULL_MASK, ny), __ballot_sync(URH_FULL_MASK, ay), lane);
+                } else {
+                    rt.feed(it + j, SRC::template cls<T>(v.x, cls, thr0), SRC::template cls<T>(v.y, cls, thr0), true, true, lane);
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 4; j++) cur[j] = nxt[j];
         }

@@ -257,7 +257,8 @@ __global__ void k_fold_prev_fired(const int64_t* __restrict__ all, int rank, int
     *xprev = v;
 }
 
-extern "C" int urh_nccl_allgather(urh_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
+int urh_coll_allgather(urh_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);   // nccl.cu: mailboxes or NCCL
+extern "C" int urh_p2p_check(urh_ctx* ctx);
 
 // ---- driver --------------------------------------------------------------------------------------------------------------
 struct FinishShard {
@@ -302,7 +303,7 @@ static int finish_tiles(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t 
     URH_CHECK((urhts::scan<RunCarry, RunCarryOp, ScanRunCarry>(ctx, ntiles, rc_ident, RunCarryOp(), fa, d_tot_run)));
     if (sharded) {
         URH_LAUNCH(ctx, k_pack_stage1, 1, 1, 0, d_init, (const RunCarry*)d_tot_run, d_msg1);
-        URH_CHECK(urh_nccl_allgather(ctx, d_msg1, d_all1, 4 * sizeof(int64_t)));
+        URH_CHECK(urh_coll_allgather(ctx, d_msg1, d_all1, 4 * sizeof(int64_t)));
         URH_LAUNCH(ctx, k_fold_carry, 1, 1, 0, (const int64_t*)d_all1, sh.rank, d_xcarry);
     }
     ScanCandidates fb;
@@ -313,7 +314,7 @@ static int finish_tiles(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t 
     URH_CHECK((urhts::scan<CandAgg, CandOp, ScanCandidates>(ctx, ntiles, ca_ident, CandOp(), fb, d_tot_cand)));
     const int16_t* prev0 = d_init;
     if (sharded) {
-        URH_CHECK(urh_nccl_allgather(ctx, d_tot_cand, d_all2, sizeof(CandAgg)));
+        URH_CHECK(urh_coll_allgather(ctx, d_tot_cand, d_all2, sizeof(CandAgg)));
         URH_LAUNCH(ctx, k_fold_prev_cls, 1, 1, 0, (const int64_t*)d_all2, sh.rank, (const int64_t*)d_all1, d_prev0);
         prev0 = d_prev0;
     }
@@ -325,7 +326,7 @@ static int finish_tiles(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t 
     URH_CHECK((urhts::scan<FireAgg, FireOp, ScanFirings, 4>(ctx, ntiles, fi_ident, FireOp(), fc, d_tot_fire)));   // heavy load(): thin blocks
     const int64_t* xprev = d_small + 2;
     if (sharded) {
-        URH_CHECK(urh_nccl_allgather(ctx, d_tot_fire, d_all3, sizeof(FireAgg)));
+        URH_CHECK(urh_coll_allgather(ctx, d_tot_fire, d_all3, sizeof(FireAgg)));
         URH_LAUNCH(ctx, k_fold_prev_fired, 1, 1, 0, (const int64_t*)d_all3, sh.rank, d_xprev);
         xprev = d_xprev;
     }
@@ -346,6 +347,7 @@ static int finish_tiles(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t 
                    (const int32_t*)prev_cls, prev0, (const int64_t*)row_off, (const int64_t*)prev_fired, xprev, ntiles, sh.global_offset,
                    sh.n_total, tol, is_ask ? 1 : 0, (int64_t)sps, sh.emit_tail, raw, raw_cap, d_small);
         URH_CHECK(urh_read_i64(ctx, d_small, 2, got));
+        if (sharded) URH_CHECK(urh_p2p_check(ctx));   // a mailbox exchange of this step (or of the center chain before it) timed out?
         if (got[0] <= raw_cap) break;
         if (attempt == 1) URH_FAIL(ctx, URH_ERR_CUDA, "finish_tiles: row buffer overflow after regrowth");
         // more rows than guessed: grow and repeat stage D only

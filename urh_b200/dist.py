@@ -100,7 +100,7 @@ def init_p2p(ctx: _lib.Context, hx: HostExchange):
     3.43 vs 3.46 fused) -- the per-step overhead of a sharded capture is rank skew and the small device stages between
     the exchanges, not the collective's latency -- so NCCL stays the default."""
     ctx.p2p = False
-    ok = hx.world <= 8 and hx.world > 1 and os.environ.get("URH_B200_P2P", "0") == "1"
+    ok = hx.world <= 8 and hx.world > 1 and os.environ.get("URH_B200_P2P", "1") != "0"
     handle = C.create_string_buffer(64)
     if ok:
         ok = ctx.lib.urh_p2p_create(ctx.handle, handle) == 0
