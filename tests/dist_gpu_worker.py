@@ -57,6 +57,32 @@ def main():
             ctx.check(ctx.lib.urh_p2p_check(ctx.handle))
             if not np.array_equal(got[:cnt], ref[:cnt]) or np.any(got[cnt:] != 0):
                 failures.append(("p2p device allreduce", it, cnt))
+        # latency of the exchanges (context timer: CUDA events on the context stream)
+        d_send = to_device(np.arange(4, dtype=np.int64), ctx)
+        d_g = DeviceArray(ctx, (world, 4), np.int64)
+        d_in = to_device(np.arange(6000, dtype=np.int64), ctx)
+        d_out = DeviceArray(ctx, (6000,), np.int64)
+        d_cnt = to_device(np.array([8], np.int64), ctx)
+        d_cnt_all = to_device(np.array([6000], np.int64), ctx)
+        lat = {}
+        for name, call in [
+            ("p2p_allgather_dev", lambda: ctx.lib.urh_p2p_allgather_dev(ctx.handle, C.c_void_p(d_send.ptr), C.c_void_p(d_g.ptr), 32)),
+            ("nccl_allgather", lambda: ctx.lib.urh_nccl_allgather(ctx.handle, C.c_void_p(d_send.ptr), C.c_void_p(d_g.ptr), 32)),
+            ("p2p_allreduce_dev[8]", lambda: ctx.lib.urh_p2p_allreduce_u64_dev(ctx.handle, C.c_void_p(d_in.ptr), C.c_void_p(d_out.ptr), C.c_void_p(d_cnt.ptr), 6000)),
+            ("p2p_allreduce_dev[6000]", lambda: ctx.lib.urh_p2p_allreduce_u64_dev(ctx.handle, C.c_void_p(d_in.ptr), C.c_void_p(d_out.ptr), C.c_void_p(d_cnt_all.ptr), 6000)),
+            ("nccl_allreduce[6000]", lambda: ctx.lib.urh_nccl_allreduce_i64(ctx.handle, C.c_void_p(d_in.ptr), 6000, 0)),
+        ]:
+            for _ in range(20):
+                ctx.check(call())
+            ctx.sync()
+            hx.barrier()
+            ctx.timer_start()
+            for _ in range(200):
+                ctx.check(call())
+            lat[name] = ctx.timer_stop() * 1000.0 / 200
+        ctx.check(ctx.lib.urh_p2p_check(ctx.handle))
+        if rank == 0:
+            print("DIST_GPU exchange latency (us per call, 200 back to back):", {k: round(v, 2) for k, v in lat.items()}, flush=True)
         for it in range(300):
             k = 1 + it % 6
             send = rng_x.integers(-2**62, 2**62, k).astype(np.int64)

@@ -382,3 +382,102 @@ struct UrhRunTracker {
         }
     }
 };
+
+// ---- whole-tile resolve for binary classifiers ---------------------------------------------------------------------------------
+// A FULL tile is 32 groups of 64 samples, and a warp has 32 lanes: while the tile streams through, lane g keeps group g's class
+// masks (UrhRunTracker::feed_masks' n0/a0/n1/a1); afterwards every lane settles the boundaries of ITS group, with one prefix-max
+// over the lanes for "where did the run that enters my group start" and one prefix-sum for the candidates' slots.  The work per
+// tile no longer depends on how the boundaries are spread (one loop iteration per boundary of the busiest group), the streaming
+// loop holds no bookkeeping at all, and the code is a fraction of the inlined group-by-group walk (instruction cache).
+// Same results as UrhRunTracker: a boundary at p closes the run [q, p) opened by its predecessor q; the run that starts at the
+// tile's first sample is the head run (head_len, no candidate); any other run longer than tol leaves the candidate (q + tol, class).
+struct UrhTileResolve {
+    uint32_t n0, a0, n1, a1;   // this lane's group
+    __device__ __forceinline__ void init() { n0 = a0 = n1 = a1 = 0u; }
+    __device__ __forceinline__ void keep(int g, uint32_t gn0, uint32_t ga0, uint32_t gn1, uint32_t ga1, int lane) {
+        if (lane == g) { n0 = gn0; a0 = ga0; n1 = gn1; a1 = ga1; }
+    }
+    __device__ __forceinline__ static int cls_of(uint32_t nbit, uint32_t abit) { return (nbit & 1u) ? -1 : (int)(abit & 1u); }
+
+    template <bool WRITE>
+    __device__ __forceinline__ int walk(uint32_t m0, uint32_t m1, uint32_t pn, uint32_t pa, int q, int tol, int lane, uint32_t* dst) const {
+        int k = 0;
+        const int base = lane * 64;
+        while (m0 | m1) {
+            const int l0 = m0 ? (__ffs(m0) - 1) : 64;
+            const int l1 = m1 ? (__ffs(m1) - 1) : 64;
+            const bool take0 = l0 <= l1;
+            const int l = take0 ? l0 : l1;
+            if (take0) m0 &= m0 - 1; else m1 &= m1 - 1;
+            const int p = base + 2 * l + (take0 ? 0 : 1);
+            if (q > 0 && p - q > tol) {      // q == 0: the head run; q < 0: p is the tile's first sample
+                if (WRITE) {
+                    // the closed run's class = the class of sample p - 1
+                    uint32_t nb, ab;
+                    if (!take0) { nb = n0 >> l; ab = a0 >> l; }
+                    else if (l > 0) { nb = n1 >> (l - 1); ab = a1 >> (l - 1); }
+                    else { nb = pn; ab = pa; }
+                    dst[k] = ((uint32_t)(q + tol) << 16) | (uint32_t)(cls_of(nb, ab) + 1);
+                }
+                k++;
+            }
+            q = p;
+        }
+        return k;
+    }
+
+    // tile_len == URH_TILE.  stage: this tile's staging slots.
+    __device__ __forceinline__ void finish(int tol, uint32_t* stage, UrhTileSummary* out, int lane) const {
+        // class bits of the sample before my group's first sample
+        const uint32_t pn = __shfl_up_sync(URH_FULL_MASK, n1 >> 31, 1), pa = __shfl_up_sync(URH_FULL_MASK, a1 >> 31, 1);
+        uint32_t m0 = (((n1 << 1) | (pn & 1u)) ^ n0) | (((a1 << 1) | (pa & 1u)) ^ a0);
+        if (lane == 0) m0 |= 1u;   // the tile's first sample opens the head run
+        const uint32_t m1 = (n0 ^ n1) | (a0 ^ a1);
+        int last = -1;             // my group's last boundary (tile-relative)
+        if (m1) last = lane * 64 + 2 * (31 - __clz(m1)) + 1;
+        if (m0) last = max(last, lane * 64 + 2 * (31 - __clz(m0)));
+        int incl = last;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(URH_FULL_MASK, incl, off);
+            if (lane >= off) incl = max(incl, t);
+        }
+        int q = __shfl_up_sync(URH_FULL_MASK, incl, 1);   // where the run entering my group started
+        if (lane == 0) q = -1;
+        const int L = __shfl_sync(URH_FULL_MASK, incl, 31);   // the tile's last boundary (>= 0: the one at sample 0)
+        // head run: ends at the first boundary after sample 0
+        uint32_t f0 = m0, f1 = m1;
+        if (lane == 0) f0 &= ~1u;
+        int first = URH_TILE;
+        if (f0 | f1) {
+            const int l0 = f0 ? (__ffs(f0) - 1) : 64, l1 = f1 ? (__ffs(f1) - 1) : 64;
+            first = lane * 64 + ((l0 <= l1) ? 2 * l0 : 2 * l1 + 1);
+        }
+        const int head_len = __reduce_min_sync(URH_FULL_MASK, first);
+        // candidates: count, slot, write
+        const int mine = walk<false>(m0, m1, pn, pa, q, tol, lane, nullptr);
+        int pre = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(URH_FULL_MASK, pre, off);
+            if (lane >= off) pre += t;
+        }
+        int total = __shfl_sync(URH_FULL_MASK, pre, 31);
+        if (mine) walk<true>(m0, m1, pn, pa, q, tol, lane, stage + (pre - mine));
+        // the run that is still open at the tile's end
+        const int last_cls = __shfl_sync(URH_FULL_MASK, cls_of(n1 >> 31, a1 >> 31), 31);
+        if (L > 0 && URH_TILE - L > tol) {
+            if (lane == 0) stage[total] = ((uint32_t)(L + tol) << 16) | (uint32_t)(last_cls + 1);
+            total++;
+        }
+        if (lane == 0) {
+            UrhTileSummary s;
+            s.first_cls = (int16_t)cls_of(n0, a0);
+            s.last_cls = (int16_t)last_cls;
+            s.head_len = head_len;
+            s.tail_len = URH_TILE - L;
+            s.ncand = total;
+            *out = s;
+        }
+    }
+};

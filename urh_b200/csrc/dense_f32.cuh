@@ -76,12 +76,42 @@ k_dense_f32(const T* __restrict__ x, int64_t n, int vec_in, const __grid_constan
         // the demodulator counted the tile's kept samples (> -4): all kept <=> no sample carries the noise sentinel (<= -4), and
         // the noise masks (half of the compares, votes and mask arithmetic) are known to be zero
         const bool no_noise = SRC::BINARY && tile_stats && cls.noise_value <= -4.0f && tile_stats[tile].cnt == URH_TILE;
-        // eight 64-groups in flight per warp (four being classified, four being loaded).  (A ring of eight, each register refilled
-        // as soon as it is consumed, was slower: eight inlined copies of the boundary path no longer fit the instruction cache.)
+        // eight 64-groups in flight per warp (four being classified, four being loaded)
         V cur[4], nxt[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) cur[j] = __ldg(p + j * 32);
         if (tile_start == 0 && lane == 0 && init_cls) *init_cls = (int16_t)(((float)cur[0].x == cls.noise_value) ? -1 : cls_of_zero);
+        if (SRC::BINARY) {
+            // stream the tile into class masks (lane g keeps group g's), settle the whole tile afterwards
+            UrhTileResolve tr;
+            tr.init();
+#pragma unroll 1
+            for (int it = 0; it < ITERS; it += 4) {
+                if (it + 4 < ITERS) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) nxt[j] = __ldg(p + (it + 4 + j) * 32);
+                }
+                if (no_noise) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        tr.keep(it + j, 0u, __ballot_sync(URH_FULL_MASK, SRC::template above<T>(cur[j].x, thr0)), 0u,
+                                __ballot_sync(URH_FULL_MASK, SRC::template above<T>(cur[j].y, thr0)), lane);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        bool nx, ax, ny, ay;
+                        SRC::template bits<T>(cur[j].x, cls, thr0, nx, ax);
+                        SRC::template bits<T>(cur[j].y, cls, thr0, ny, ay);
+                        tr.keep(it + j, __ballot_sync(URH_FULL_MASK, nx), __ballot_sync(URH_FULL_MASK, ax), __ballot_sync(URH_FULL_MASK, ny),
+                                __ballot_sync(URH_FULL_MASK, ay), lane);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) cur[j] = nxt[j];
+            }
+            tr.finish(tol, staging + tile * (int64_t)stage_cap, tiles + tile, lane);
+            return;
+        }
 #pragma unroll 1
         for (int it = 0; it < ITERS; it += 4) {
             if (it + 4 < ITERS) {
@@ -89,21 +119,8 @@ k_dense_f32(const T* __restrict__ x, int64_t n, int vec_in, const __grid_constan
                 for (int j = 0; j < 4; j++) nxt[j] = __ldg(p + (it + 4 + j) * 32);
             }
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const V v = cur[j];
-                if (SRC::BINARY && no_noise) {
-                    rt.feed_masks(it + j, 0u, __ballot_sync(URH_FULL_MASK, SRC::template above<T>(v.x, thr0)), 0u,
-                                  __ballot_sync(URH_FULL_MASK, SRC::template above<T>(v.y, thr0)), lane);
-                } else if (SRC::BINARY) {
-                    bool nx, ax, ny, ay;
-                    SRC::template bits<T>(v.x, cls, thr0, nx, ax);
-                    SRC::template bits<T>(v.y, cls, thr0, ny, ay);
-                    rt.feed_masks(it + j, __ballot_sync(URH_FULL_MASK, nx), __ballot_sync(URH_FULL_MASK, ax),
-                                  __ballot_sync(URH_FULL_MASK, ny), __ballot_sync(URH_FULL_MASK, ay), lane);
-                } else {
-                    rt.feed(it + j, SRC::template cls<T>(v.x, cls, thr0), SRC::template cls<T>(v.y, cls, thr0), true, true, lane);
-                }
-            }
+            for (int j = 0; j < 4; j++)
+                rt.feed(it + j, SRC::template cls<T>(cur[j].x, cls, thr0), SRC::template cls<T>(cur[j].y, cls, thr0), true, true, lane);
 #pragma unroll
             for (int j = 0; j < 4; j++) cur[j] = nxt[j];
         }

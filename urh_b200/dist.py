@@ -94,13 +94,15 @@ def init_nccl(ctx: _lib.Context, hx: HostExchange):
 
 
 def init_p2p(ctx: _lib.Context, hx: HostExchange):
-    """NVLink peer mailboxes for the few-bytes all-gathers (p2p.cu).  Used only if EVERY rank could map every peer
-    (one node, <= 8 GPUs, CUDA IPC available); otherwise those exchanges stay on NCCL.
-    Opt-in with URH_B200_P2P=1: measured on par with the NCCL path at 2 GPUs (5.23 vs 5.22 ms/step with center detection,
-    3.43 vs 3.46 fused) -- the per-step overhead of a sharded capture is rank skew and the small device stages between
-    the exchanges, not the collective's latency -- so NCCL stays the default."""
+    """NVLink peer mailboxes for the few-bytes exchanges (p2p.cu): host-side all-gathers and the device-resident, stream-ordered
+    all-gather / histogram sum the sharded chains use between their kernels.  Used only if EVERY rank could map every peer (one
+    node, <= 8 GPUs, CUDA IPC available); otherwise those exchanges stay on NCCL.
+    Opt-in with URH_B200_P2P=1.  Measured at 2 GPUs (round 2): 8.3 us per device all-gather against 7.2 us for NCCL's, 9.1 / 14.9 us
+    for the histogram sum of 8 / 6000 words against 10.4 us; the step is 4.23 ms with the mailboxes and 4.21 ms with NCCL -- the
+    per-step cost of a sharded capture is rank skew and the small device stages between the exchanges, not the collective's
+    latency -- so NCCL stays the default."""
     ctx.p2p = False
-    ok = hx.world <= 8 and hx.world > 1 and os.environ.get("URH_B200_P2P", "1") != "0"
+    ok = hx.world <= 8 and hx.world > 1 and os.environ.get("URH_B200_P2P", "0") == "1"
     handle = C.create_string_buffer(64)
     if ok:
         ok = ctx.lib.urh_p2p_create(ctx.handle, handle) == 0
