@@ -596,7 +596,7 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     dense = float(np.mean(dense_ms))
     achieved = ALG_BYTES_PER_SAMPLE * n / (dense * 1e-3) / 1e9
-    kernel_key = "k_fsk_fast<F32,WRITE,STATS>" if args.center == "detect" else "k_fsk_fast<F32,DIGITIZE,WRITE>"
+    kernel_key = "k_fsk_fifo<WRITE,STATS>" if args.center == "detect" else "k_fsk_fifo<DIGITIZE,WRITE>"
     traffic, traffic_src = None, None
     try:
         tj = json.load(open(TRAFFIC_FILE))

@@ -119,7 +119,7 @@ k_fsk_fast(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
 }
 
 // The same kernel with the input staged through the shared-memory FIFO (float32 captures).
-#define URH_FSK_FIFO 6
+#define URH_FSK_FIFO 3
 template <bool DIGITIZE, bool WRITE, bool STATS>
 __global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32, 5)
 k_fsk_fifo(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __restrict__ qad_out, float thr0,
