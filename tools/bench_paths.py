@@ -74,6 +74,18 @@ def main():
                                 C.c_double(B.FDEV / B.FS), 1.0, B.SIGMA, 99, 6_000_000, 5_000_000, int(0.40 * n), int(0.43 * n), int(0.97 * n)))
     ctx.sync()
 
+    # the SDR-native sample formats (2^26-sample slice of the same capture, scaled to the integer range)
+    ni = min(n, 1 << 26)
+    host = d_iq[:ni].get()
+    for dt, scale, noise in ((np.int16, 8000.0, B.NOISE_MAG * 8000.0), (np.int8, 100.0, B.NOISE_MAG * 100.0)):
+        d_i = to_device(np.ascontiguousarray(np.round(host * scale).astype(dt)), ctx)
+        d_qi = DeviceArray(ctx, (ni,), np.float32)
+        k = C.c_int64(0)
+        run = lambda: ctx.check(lib.urh_demod_digitize(ctx.handle, C.c_void_p(d_i.ptr), _lib.dtype_code(dt), ni, float(noise), _lib.MOD_FSK, 0.0, 5, B.SPS, 1,
+                                                       0.1, C.c_void_p(d_qi.ptr), C.byref(k)))
+        emit("demod + digitize FSK, %s capture (fused, center given)" % np.dtype(dt).name, timed(ctx, run), ni, 2 * np.dtype(dt).itemsize + 4)
+        del d_i, d_qi
+    del host
     q = sf.afp_demod(d_iq, B.NOISE_MAG, "FSK", 2)
     emit("afp_demod FSK (exact, no digitizer)", timed(ctx, lambda: sf.afp_demod(d_iq, B.NOISE_MAG, "FSK", 2)), n, 12)
     emit("afp_demod ASK", timed(ctx, lambda: sf.afp_demod(d_iq, B.NOISE_MAG, "ASK", 2)), n, 12)

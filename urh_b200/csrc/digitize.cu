@@ -118,14 +118,14 @@ k_fsk_fast(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
                                                   STATS ? tile_stats + tile : nullptr, 0u, DIGITIZE ? tiles + tile : nullptr);
 }
 
-// The same kernel with the input staged through the shared-memory FIFO (float32 captures).
+// The same kernel with the input staged through the shared-memory FIFO.
 #define URH_FSK_FIFO 3
-template <bool DIGITIZE, bool WRITE, bool STATS>
-__global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32, 5)
+template <int DT, bool DIGITIZE, bool WRITE, bool STATS>
+__global__ void __launch_bounds__(URH_WARPS_PER_BLOCK * 32, (DT == URH_DT_F32) ? 5 : 4)   // (the integer variants spill at 48 registers)
 k_fsk_fifo(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __restrict__ qad_out, float thr0,
            float cls_noise, int tol, UrhTileSummary* __restrict__ tiles, uint32_t* __restrict__ staging, int stage_cap,
            int64_t tile_begin, int64_t tile_count, UrhTileStats* __restrict__ tile_stats) {
-    __shared__ __align__(16) unsigned char s_fifo[URH_WARPS_PER_BLOCK][URH_FSK_FIFO + 1][512];
+    __shared__ __align__(16) unsigned char s_fifo[URH_WARPS_PER_BLOCK][URH_FSK_FIFO + 1][64 * 2 * sizeof(typename UrhElem<DT>::type)];
     const int lane = threadIdx.x & 31;
     const int64_t tile_rel = (int64_t)blockIdx.x * URH_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (tile_rel >= tile_count) return;
@@ -136,7 +136,7 @@ k_fsk_fifo(const void* __restrict__ iq, int64_t n, UrhDemodParams dp, float* __r
     one.p = dp.one;
     one.m = dp.mone;
     const uint32_t fifo = (uint32_t)__cvta_generic_to_shared(&s_fifo[threadIdx.x >> 5][0][0]);
-    urh_fsk_full_tile<URH_DT_F32, DIGITIZE, WRITE, STATS, URH_FSK_FIFO>(iq, n, tile * URH_TILE, dp, qad_out, thr0, cls_noise, rt, lane, one,
+    urh_fsk_full_tile<DT, DIGITIZE, WRITE, STATS, URH_FSK_FIFO>(iq, n, tile * URH_TILE, dp, qad_out, thr0, cls_noise, rt, lane, one,
                                                                         STATS ? tile_stats + tile : nullptr, fifo,
                                                                         DIGITIZE ? tiles + tile : nullptr);
 }
@@ -219,21 +219,21 @@ static int launch_dense_iq_t(urh_ctx* ctx, const void* d_iq, int64_t n, const Ur
         const int64_t fb = tile_lo > 1 ? tile_lo : 1, fe = tile_hi < nfull ? tile_hi : nfull;
         if (fe > fb) {
             const unsigned grid = (unsigned)urh_div_up(fe - fb, URH_WARPS_PER_BLOCK);
-            // float32 captures: the variant that stages its input through the shared-memory FIFO (2360 vs 2417 us at 2^30 samples)
+            // the variant that stages its input through the shared-memory FIFO (float32: 2230 vs 2417 us at 2^30 samples)
             static const bool fifo = getenv("URH_B200_FSK_NO_FIFO") == nullptr;
-            const bool ff = fifo && DT == URH_DT_F32;
+            const bool ff = fifo;
             if (tile_stats && d_qad && !DIG) {
-                if (ff) URH_LAUNCH(ctx, (k_fsk_fifo<false, true, true>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
+                if (ff) URH_LAUNCH(ctx, (k_fsk_fifo<DT, false, true, true>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
                                    tiles, staging, stage_cap, fb, fe - fb, tile_stats);
                 else URH_LAUNCH(ctx, (k_fsk_fast<DT, false, true, true>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value,
                                 tol, tiles, staging, stage_cap, fb, fe - fb, tile_stats);
             } else if (d_qad) {
-                if (ff) URH_LAUNCH(ctx, (k_fsk_fifo<DIG, true, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
+                if (ff) URH_LAUNCH(ctx, (k_fsk_fifo<DT, DIG, true, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
                                    tiles, staging, stage_cap, fb, fe - fb, nullptr);
                 else URH_LAUNCH(ctx, (k_fsk_fast<DT, DIG, true, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
                                 tiles, staging, stage_cap, fb, fe - fb, nullptr);
             } else {
-                if (ff) URH_LAUNCH(ctx, (k_fsk_fifo<DIG, false, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
+                if (ff) URH_LAUNCH(ctx, (k_fsk_fifo<DT, DIG, false, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
                                    tiles, staging, stage_cap, fb, fe - fb, nullptr);
                 else URH_LAUNCH(ctx, (k_fsk_fast<DT, DIG, false, false>), grid, threads, 0, d_iq, n, dp, d_qad, cls.thr[0], cls.noise_value, tol,
                                 tiles, staging, stage_cap, fb, fe - fb, nullptr);
