@@ -5,3 +5,6 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
 timeout 600 python bench.py --steps 20 --warmup 3 --worst > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_refarm.json 2> gpurun_out/r02_bench_refarm.err
 tail -c 600 gpurun_out/r02_bench_refarm.json
+timeout 600 python tools/bench_paths.py > gpurun_out/r02_secondary.jsonl 2> gpurun_out/r02_secondary.err
+timeout 600 python tools/bench_configs.py > gpurun_out/r02_configs.jsonl 2> gpurun_out/r02_configs.err
+tail -2 gpurun_out/r02_configs.err
