@@ -55,6 +55,16 @@ def env_int(name, default):
         return default
 
 
+def capture_gaps(n, rank):
+    """Every 2^log2n-sample block of the capture has the same structure: bursts of 5 M samples every 6 M, one long gap at 40-43 % of
+    the block and silence from 97 % on.  One block per GPU: the per-GPU work is the same at every N (weak scaling).  With the long
+    gap and the tail defined on the WHOLE capture instead, two of eight shards hold them all and the other six do 8 % more work in
+    the histogram and digitizer passes than the single-GPU run (silent tiles are skipped): measured with tools/timeline_dist.py,
+    profiles/r02_timeline_n4_globalgaps_*.json - 318 of the 390 us a step lost from 1 to 8 GPUs were that imbalance, 87 us the exchanges."""
+    off = n * rank
+    return off + int(0.40 * n), off + int(0.43 * n), off + int(0.97 * n)
+
+
 def make_symbols(nsym, seed):
     rng = np.random.Generator(np.random.PCG64(seed))
     b = (rng.integers(0, 2, nsym, dtype=np.int8) * 2 - 1).astype(np.int8)
@@ -285,7 +295,8 @@ def main():
     world = env_int("WORLD_SIZE", 1)
     n = 1 << args.log2n
     layout = ("2^%d samples on one GPU" % args.log2n if world == 1 else
-              "ONE capture of %d x 2^%d samples sharded by contiguous range (1-sample halo, run stitching across shards)" % (world, args.log2n))
+              "ONE capture of %d x 2^%d samples (every 2^%d-sample block built like the single-GPU capture) sharded by contiguous range "
+              "(1-sample halo, run stitching across shards)" % (world, args.log2n, args.log2n))
     workload = ("2-FSK complex64, %s @2MS/s sps=100 +-100kHz AWGN sigma=0.01 bursts+gaps; %s (tol=5, noise=0.05)"
                 % (layout, "demod + detect_center (capture-wide) + digitize" if args.center == "detect"
                    else "fused demod+digitize, center=0 given"))
@@ -336,8 +347,7 @@ def main():
     d_qad = DeviceArray(ctx, (n,), np.float32)
     period, burst = 6_000_000, 5_000_000
     ctx.check(lib.urh_synth_fsk(ctx.handle, C.c_void_p(d_iq.ptr), n, offset, SPS, C.c_void_p(d_b.ptr), C.c_void_p(d_s.ptr),
-                                C.c_double(FDEV / FS), 1.0, SIGMA, 12345, period, burst,
-                                int(0.40 * n_total), int(0.43 * n_total), int(0.97 * n_total)))
+                                C.c_double(FDEV / FS), 1.0, SIGMA, 12345, period, burst, *capture_gaps(n, rank)))
     ctx.sync()
     if world > 1:
         hx = udist.HostExchange()
@@ -563,8 +573,7 @@ def main():
                  ("white-noise IQ (sigma = 1, no carrier), noise gate off: random angles, ~70 % of the pairs on the scalar path", 0.0, 0.0, 1.0, 0.0)]
         for name, dev, amp, sigma, noise in cases:
             ctx.check(lib.urh_synth_fsk(ctx.handle, C.c_void_p(d_iq.ptr), n, offset, SPS, C.c_void_p(d_b.ptr), C.c_void_p(d_s.ptr),
-                                        C.c_double(dev), amp, sigma, 777, period, burst, int(0.40 * n_total), int(0.43 * n_total),
-                                        int(0.97 * n_total)))
+                                        C.c_double(dev), amp, sigma, 777, period, burst, *capture_gaps(n, rank)))
             ctx.sync()
             k = C.c_int64(0)
 

@@ -279,6 +279,10 @@ int urh_p2p_check(urh_ctx* ctx);
 /* ---- measurement utilities (not part of the reference's API surface) -------------------------------- */
 /* CUDA-event timing of the dominant (dense, sample-rate) kernel of the last demod/digitize call */
 int urh_set_profiling(urh_ctx* ctx, int enabled);
+/* urh_set_profiling(ctx, 2) also records a stream timeline of the sharded one-call step: CUDA events at the step's start, on
+ * either side of every inter-GPU exchange and after the rows are written.  urh_timeline_fetch (after the step's result has been
+ * read) returns the milliseconds from the first mark to each mark and the '\n'-separated names; *count = number of marks (<= 32). */
+int urh_timeline_fetch(urh_ctx* ctx, float* h_ms, char* h_names, int names_cap, int* count);
 int urh_last_dense_ms(urh_ctx* ctx, float* ms);
 /* speculative Costas loop diagnostics of the last PSK demodulation: {chunks matched in O(1), chunks walked, samples stepped serially} */
 int urh_costas_stats(urh_ctx* ctx, int64_t* h_out3);

@@ -71,6 +71,7 @@ SIGNATURES = {
     "urh_host_free": (i32, [vp, vp]),
     "urh_timer_start": (i32, [vp]),
     "urh_timer_stop": (i32, [vp, C.POINTER(f32)]),
+    "urh_timeline_fetch": (i32, [vp, vp, vp, i32, C.POINTER(i32)]),
     "urh_launch_count": (i64, [vp]),
     "urh_afp_demod": (i32, [vp, vp, i32, i64, f32, i32, i32, f32, vp]),
     "urh_get_center_thresholds": (i32, [f32, f32, i32, vp]),

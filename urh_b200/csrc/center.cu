@@ -912,14 +912,18 @@ int urh_center_chain(urh_ctx* ctx, const float* d_qad, int64_t n, const UrhTileS
     URH_CHECK((urhts::scan<int64_t, CenAddI64, ScanKept>(ctx, ntiles, (int64_t)0, CenAddI64(), fk, prefix + ntiles)));
     const int64_t* counts = prefix + ntiles;
     if (world > 1) {
+        URH_TL_MARK(ctx, "x1 kept counts: enter");
         URH_CHECK(urh_coll_allgather(ctx, prefix + ntiles, d_counts, sizeof(int64_t)));
+        URH_TL_MARK(ctx, "x1 kept counts: done");
         counts = d_counts;
     }
     URH_LAUNCH(ctx, k_center_ranks, 1, 1, 0, counts, rank, world, max_size, plan);
     URH_LAUNCH(ctx, k_center_window, nb, 256, 0, d_qad, n, ts, (const int64_t*)prefix, ntiles, plan, partial);
     const CenStats* parts = &plan->local;
     if (world > 1) {
+        URH_TL_MARK(ctx, "x2 window partials: enter");
         URH_CHECK(urh_coll_allgather(ctx, &plan->local, d_parts, sizeof(CenStats)));
+        URH_TL_MARK(ctx, "x2 window partials: done");
         parts = d_parts;
     }
     URH_LAUNCH(ctx, k_center_plan, 1, 256, 0, parts, world, plan, fe, hist);
@@ -929,6 +933,7 @@ int urh_center_chain(urh_ctx* ctx, const float* d_qad, int64_t n, const UrhTileS
     URH_LAUNCH(ctx, (k_hist_interior_dev<false>), gs, 256, dyn, d_qad, n, (const CenterPlan*)plan, (const float*)fe, hist, (const int64_t*)prefix);
     URH_LAUNCH(ctx, k_hist_window_ends_dev, 2, 256, 0, d_qad, n, (const int64_t*)prefix, (const CenterPlan*)plan, (const float*)fe, hist);
     const unsigned long long* hist_all = hist;
+    if (world > 1) URH_TL_MARK(ctx, "x3 histogram sum: enter");
     if (world > 1) {
         if (urh_p2p_usable(ctx, 8)) {   // NVLink mailboxes: only the plan's nbins words travel
             unsigned long long* hist_sum;
@@ -939,6 +944,7 @@ int urh_center_chain(urh_ctx* ctx, const float* d_qad, int64_t n, const UrhTileS
             URH_CHECK(urh_nccl_allreduce_i64(ctx, (int64_t*)hist, CEN_MAX_BINS, 0));
         }
     }
+    if (world > 1) URH_TL_MARK(ctx, "x3 histogram sum: done");
     URH_LAUNCH(ctx, k_center_pick, 1, 256, 0, hist_all, plan);
     ctx->center_prefix = prefix;
     ctx->center_ts = ts;

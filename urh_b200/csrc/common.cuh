@@ -26,6 +26,10 @@ struct urh_ctx {
     cudaEvent_t ev_k0, ev_k1;  // around the dense kernel when profiling is on
     int profiling;
     int dense_timed;
+    // stream timeline (urh_set_profiling(ctx, 2)): events recorded at named points of the sharded step
+    cudaEvent_t tl_ev[32];
+    const char* tl_name[32];
+    int tl_count, tl_ready;
     char err[512];
     int64_t launches;
     // grow-only scratch arena: bump allocation inside a list of blocks, reset at the start of each op
@@ -119,6 +123,10 @@ struct urh_ctx {
         URH_CUDA(ctx, cudaGetLastError());                                                \
     } while (0)
 
+// stream timeline: mark a point of the step (profiling level 2 only; no effect otherwise)
+#define URH_TL_MARK(ctx, label) do { if ((ctx)->profiling >= 2 && (ctx)->tl_ready && (ctx)->tl_count < 32) { \
+        (ctx)->tl_name[(ctx)->tl_count] = (label); cudaEventRecord((ctx)->tl_ev[(ctx)->tl_count++], (ctx)->stream); } } while (0)
+#define URH_TL_RESET(ctx) do { (ctx)->tl_count = 0; } while (0)
 // record events around the dense kernel when profiling is enabled
 #define URH_PROF_BEGIN(ctx) do { if ((ctx)->profiling) cudaEventRecord((ctx)->ev_k0, (ctx)->stream); } while (0)
 #define URH_PROF_END(ctx) do { if ((ctx)->profiling) { cudaEventRecord((ctx)->ev_k1, (ctx)->stream); (ctx)->dense_timed = 1; } } while (0)

@@ -76,6 +76,8 @@ extern "C" int urh_ctx_create(int device, urh_ctx** out) {
     ok = ok && cudaEventCreate(&ctx->ev_k0) == cudaSuccess && cudaEventCreate(&ctx->ev_k1) == cudaSuccess;
     ctx->profiling = 0;
     ctx->dense_timed = 0;
+    ctx->tl_count = 0;
+    ctx->tl_ready = 0;
     ok = ok && cudaHostAlloc((void**)&ctx->h_mail, 64 * sizeof(int64_t), cudaHostAllocDefault) == cudaSuccess;
     if (!ok) {
         delete ctx;
@@ -196,8 +198,31 @@ extern "C" int urh_timer_stop(urh_ctx* ctx, float* ms) {
 }
 
 extern "C" int urh_set_profiling(urh_ctx* ctx, int enabled) {
-    ctx->profiling = enabled ? 1 : 0;
+    ctx->profiling = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
     ctx->dense_timed = 0;
+    if (ctx->profiling >= 2 && !ctx->tl_ready) {
+        for (int i = 0; i < 32; i++) URH_CUDA(ctx, cudaEventCreate(&ctx->tl_ev[i]));
+        ctx->tl_ready = 1;
+    }
+    ctx->tl_count = 0;
+    return URH_OK;
+}
+
+// Timeline of the last sharded step (profiling level 2): milliseconds from the step's first mark to each mark, and the marks' names
+// ('\n'-separated, into h_names).  Call after the step's result has been read (the stream is idle).
+extern "C" int urh_timeline_fetch(urh_ctx* ctx, float* h_ms, char* h_names, int names_cap, int* count) {
+    if (!count) return URH_ERR_INVALID;
+    *count = 0;
+    if (ctx->profiling < 2 || ctx->tl_count == 0) return URH_OK;
+    URH_CUDA(ctx, cudaEventSynchronize(ctx->tl_ev[ctx->tl_count - 1]));
+    int pos = 0;
+    for (int i = 0; i < ctx->tl_count; i++) {
+        float t = 0.f;
+        URH_CUDA(ctx, cudaEventElapsedTime(&t, ctx->tl_ev[0], ctx->tl_ev[i]));
+        if (h_ms) h_ms[i] = t;
+        if (h_names) pos += snprintf(h_names + pos, pos < names_cap ? (size_t)(names_cap - pos) : 0, "%s\n", ctx->tl_name[i]);
+    }
+    *count = ctx->tl_count;
     return URH_OK;
 }
 

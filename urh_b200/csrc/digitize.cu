@@ -583,6 +583,8 @@ static int demod_center_digitize_impl(urh_ctx* ctx, const void* d_iq, int dtype,
     if (urh_iq_bytes(dtype) == 0) URH_FAIL(ctx, URH_ERR_DTYPE, "Unsupported dtype");
     if (sharded && !ctx->nccl_comm) URH_FAIL(ctx, URH_ERR_INVALID, "NCCL communicator not initialised (urh_nccl_init)");
     urh_arena_reset(ctx);
+    URH_TL_RESET(ctx);
+    URH_TL_MARK(ctx, "step start");
     const UrhDemodParams dp = make_demod_params(noise_mag, mod_type, dtype);
     UrhClassify cls;
     memset(&cls, 0, sizeof(cls));

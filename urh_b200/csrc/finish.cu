@@ -303,7 +303,9 @@ static int finish_tiles(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t 
     URH_CHECK((urhts::scan<RunCarry, RunCarryOp, ScanRunCarry>(ctx, ntiles, rc_ident, RunCarryOp(), fa, d_tot_run)));
     if (sharded) {
         URH_LAUNCH(ctx, k_pack_stage1, 1, 1, 0, d_init, (const RunCarry*)d_tot_run, d_msg1);
+        URH_TL_MARK(ctx, "x4 run carry: enter");
         URH_CHECK(urh_coll_allgather(ctx, d_msg1, d_all1, 4 * sizeof(int64_t)));
+        URH_TL_MARK(ctx, "x4 run carry: done");
         URH_LAUNCH(ctx, k_fold_carry, 1, 1, 0, (const int64_t*)d_all1, sh.rank, d_xcarry);
     }
     ScanCandidates fb;
@@ -314,7 +316,9 @@ static int finish_tiles(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t 
     URH_CHECK((urhts::scan<CandAgg, CandOp, ScanCandidates>(ctx, ntiles, ca_ident, CandOp(), fb, d_tot_cand)));
     const int16_t* prev0 = d_init;
     if (sharded) {
+        URH_TL_MARK(ctx, "x5 candidates: enter");
         URH_CHECK(urh_coll_allgather(ctx, d_tot_cand, d_all2, sizeof(CandAgg)));
+        URH_TL_MARK(ctx, "x5 candidates: done");
         URH_LAUNCH(ctx, k_fold_prev_cls, 1, 1, 0, (const int64_t*)d_all2, sh.rank, (const int64_t*)d_all1, d_prev0);
         prev0 = d_prev0;
     }
@@ -326,7 +330,9 @@ static int finish_tiles(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t 
     URH_CHECK((urhts::scan<FireAgg, FireOp, ScanFirings, 4>(ctx, ntiles, fi_ident, FireOp(), fc, d_tot_fire)));   // heavy load(): thin blocks
     const int64_t* xprev = d_small + 2;
     if (sharded) {
+        URH_TL_MARK(ctx, "x6 firings: enter");
         URH_CHECK(urh_coll_allgather(ctx, d_tot_fire, d_all3, sizeof(FireAgg)));
+        URH_TL_MARK(ctx, "x6 firings: done");
         URH_LAUNCH(ctx, k_fold_prev_fired, 1, 1, 0, (const int64_t*)d_all3, sh.rank, d_xprev);
         xprev = d_xprev;
     }
@@ -346,6 +352,7 @@ static int finish_tiles(urh_ctx* ctx, int64_t n, int tol, bool is_ask, uint32_t 
         URH_LAUNCH(ctx, k_finish_rows, (unsigned)urh_div_up(ntiles, 256), 256, 0, tiles, staging, stage_cap, (const int32_t*)head_rel,
                    (const int32_t*)prev_cls, prev0, (const int64_t*)row_off, (const int64_t*)prev_fired, xprev, ntiles, sh.global_offset,
                    sh.n_total, tol, is_ask ? 1 : 0, (int64_t)sps, sh.emit_tail, raw, raw_cap, d_small);
+        if (sharded && attempt == 0) URH_TL_MARK(ctx, "rows written");
         URH_CHECK(urh_read_i64(ctx, d_small, 2, got));
         if (sharded) URH_CHECK(urh_p2p_check(ctx));   // a mailbox exchange of this step (or of the center chain before it) timed out?
         if (got[0] <= raw_cap) break;
