@@ -2,7 +2,7 @@
 """SASS evidence for profiles/: opcode histogram + the hottest basic block (by static size heuristics: the longest run of
 arithmetic between two branches) of one kernel in a built object.
 
-    python tools/sass_excerpt.py urh_b200/build/digitize.o 'k_fsk_fastILi4ELb0ELb1ELb1' > profiles/r02_sass_k_fsk_fast_stats.txt"""
+    python tools/sass_excerpt.py urh_b200/build/digitize.o 'k_fsk_fifoILi4ELb0ELb1ELb1' > profiles/r02_sass_k_fsk_fifo_stats.txt"""
 import collections
 import re
 import subprocess
