@@ -72,26 +72,29 @@ def merge_plateaus(plateaus, tolerance: int, max_count: int) -> np.ndarray:
 
 
 def get_threshold_divisor_histogram(plateau_lengths, threshold: float = 0.2) -> np.ndarray:
-    """auto_interpretation.pyx:113-143 — for every pair, count the smaller value if max/min is within `threshold`
-    above an integer.  O(L^2) on the (rounded, merged) plateau table of one message: vectorised numpy on the host."""
+    """auto_interpretation.pyx:113-143 — for every pair (i < j) of non-zero lengths, count the smaller value if max/min is within
+    `threshold` above an integer.  The test depends on the two VALUES only, so the O(L^2) pair loop folds into the (few) distinct
+    values with their multiplicities: c_a * c_b pairs for two different values, c_a (c_a - 1) / 2 for a value with itself (whose
+    quotient is exactly 1, always counted).  Same counts as the reference's loop; a message with thousands of rounded plateaus
+    costs microseconds instead of the quadratic loop (0.2 s per message in the sharded estimate of configs[4])."""
     pl = np.asarray(plateau_lengths, dtype=np.uint64)
     hist = np.zeros(int(np.max(pl)) + 1, dtype=np.uint64)
-    L = len(pl)
-    if L < 2:
+    if len(pl) < 2:
         return hist
-    thr = float(np.float32(threshold))
-    x = pl.astype(np.float64)
-    for i in range(L - 1):
-        xi = pl[i]
-        if xi == 0:
-            continue
-        rest = pl[i + 1:]
-        nz = rest != 0
-        mn = np.minimum(rest, xi)[nz]
-        mx = np.maximum(rest, xi)[nz]
-        ok = (mx.astype(np.float64) / mn.astype(np.float64) - (mx // mn).astype(np.float64)) < thr
-        np.add.at(hist, mn[ok].astype(np.int64), 1)
-    del x
+    thr = float(np.float32(threshold))   # the reference compares a double with its float parameter
+    u, c = np.unique(pl[pl != 0], return_counts=True)   # ascending
+    if len(u) == 0:
+        return hist
+    c = c.astype(np.uint64)
+    hist[u.astype(np.int64)] += c * (c - np.uint64(1)) // np.uint64(2)
+    block = 2048   # rows of the value-pair matrix per step (bounded memory for unrounded tables)
+    for lo in range(0, len(u) - 1, block):
+        mn = u[lo:lo + block, None]
+        mx = u[None, :]
+        upper = np.arange(len(u))[None, :] > np.arange(lo, min(lo + block, len(u)))[:, None]
+        ok = upper & ((mx.astype(np.float64) / mn.astype(np.float64) - (mx // mn).astype(np.float64)) < thr)
+        add = (ok * c[None, :]).sum(axis=1, dtype=np.uint64) * c[lo:lo + block]
+        hist[u[lo:lo + block].astype(np.int64)] += add
     return hist
 
 
