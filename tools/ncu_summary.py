@@ -40,12 +40,16 @@ def main():
     ap.add_argument("--samples", type=float, default=0, help="samples one launch processes (for per-sample figures)")
     ap.add_argument("--bytes-per-sample", type=float, default=0, help="algorithmic bytes per sample (SURVEY 8d)")
     ap.add_argument("--peak-gbs", type=float, default=6574.1)
+    ap.add_argument("--traffic-json", default="", help="also write the DRAM bytes per sample of the demodulation kernels (bench.py's "
+                    "roofline.traffic): {detect: k_fsk_fifo<WRITE,STATS>, given: k_fsk_fifo<DIGITIZE,WRITE>}; needs --samples")
+    ap.add_argument("--capture-note", default="", help="where the capture is summarised (recorded in the traffic file)")
     args = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", args.report, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
     print("source: %s (ncu --page raw)" % args.report)
+    traffic = {}
     for d in data:
         print("\n== " + d[col["Kernel Name"]][:150])
         for w in WANT:
@@ -56,6 +60,11 @@ def main():
             rd = to_bytes(d[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
             wr = to_bytes(d[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
             print("  %-72s %.1f GB/s (%.1f %% of %.1f)" % ("derived: DRAM traffic / duration", (rd + wr) / t / 1e9, 100 * (rd + wr) / t / 1e9 / args.peak_gbs, args.peak_gbs))
+            name = d[col["Kernel Name"]]
+            if args.samples and "k_fsk_fifo<4, 0, 1, 1>" in name:
+                traffic["detect"] = {"kernel": "k_fsk_fifo<F32,WRITE,STATS>", "dram_bytes_per_sample": (rd + wr) / args.samples, "capture": args.capture_note}
+            if args.samples and "k_fsk_fifo<4, 1, 1, 0>" in name:
+                traffic["given"] = {"kernel": "k_fsk_fifo<F32,DIGITIZE,WRITE>", "dram_bytes_per_sample": (rd + wr) / args.samples, "capture": args.capture_note}
             if args.samples and args.bytes_per_sample:
                 alg = args.samples * args.bytes_per_sample
                 print("  %-72s %.3f GB -> %.1f GB/s (%.1f %%); DRAM traffic / algorithmic = %.3f" % (
@@ -65,6 +74,11 @@ def main():
                 print("  %-72s %.1f" % ("derived: thread instructions per sample", inst * 32 / args.samples))
         except (KeyError, ValueError, ZeroDivisionError):
             pass
+    if args.traffic_json and traffic:
+        import json
+
+        with open(args.traffic_json, "w") as fh:
+            json.dump(traffic, fh, indent=1)
     return 0
 
 
